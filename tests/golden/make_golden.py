@@ -1,0 +1,204 @@
+"""Generate tests/golden/*.npz by running the REAL reference (wangronin/Bayesian-Optimization at
+/root/reference) in the build container.  Run once:  ``python tests/golden/make_golden.py [--big]``.
+
+The reference holds no numeric vectors for this path, so these files ARE the pin:
+fixed-theta fit (oracle recipe (1) of SURVEY.md §8c) + ``GaussianProcess.predict`` + the acquisition
+classes called one row at a time (the only way EI / MGFI / EpsilonPI run upstream).
+"""
+from __future__ import annotations
+
+import functools
+import os
+import sys
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+from oracle import gp_oracle as go  # noqa: E402  (only for the canonical-input recipe + ids)
+from oracle import ref_loader  # noqa: E402
+
+ns = ref_loader.load()
+
+CORR = {
+    go.CORR_RBF: "squared_exponential",
+    go.CORR_MATERN32: "matern",
+    go.CORR_MATERN52: functools.partial(ns.matern, nu=2.5),
+    go.CORR_MATERN12: functools.partial(ns.matern, nu=0.5),
+    go.CORR_ABSEXP: "absolute_exponential",
+    go.CORR_CUBIC: "cubic",
+}
+
+
+def make_gp(corr, D, mode, ok, nugget, beta=0.0, trend=go.TREND_CONSTANT):
+    tcls = {go.TREND_CONSTANT: ns.constant_trend, go.TREND_LINEAR: ns.linear_trend}[trend]
+    mean = tcls(D) if ok else tcls(D, beta=beta)
+    kw = dict(mean=mean, corr=CORR[corr], thetaL=[1e-5] * D, thetaU=[1e2] * D)
+    if mode == go.MODE_NOISELESS:
+        kw.update(nugget=None)
+    elif mode == go.MODE_NOISY:
+        kw.update(nugget=nugget)
+    else:
+        kw.update(nugget=nugget, noise_estim=True)
+    return ns.GaussianProcess(**kw)
+
+
+def acq_rows(cls, gp, Xc, **par):
+    f = cls(model=gp, **par)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return np.array([float(np.sum(f(x))) for x in Xc])
+
+
+def run_case(X, y, Xc, corr, theta, mode, ok, sigma2_or_alpha, nugget, beta=0.0, trend=go.TREND_CONSTANT,
+             minimize=True, with_grad=False, keep_L=False, t=2.0, alpha_ucb=0.5, eps=0.05, n_pg=0):
+    D = X.shape[1]
+    gp = make_gp(corr, D, mode, ok, nugget, beta, trend)
+    llf = ref_loader.fixed_theta_fit(gp, X, y, theta, sigma2_or_alpha)
+    out = dict(
+        X=X, y=y, Xc=Xc, corr=corr, theta=np.asarray(theta, float), mode=mode, ok=ok,
+        par_last=np.nan if sigma2_or_alpha is None else sigma2_or_alpha,
+        nugget=0.0 if nugget is None else nugget, beta_in=beta, trend=trend, minimize=minimize,
+        llf=llf,
+    )
+    if not np.isfinite(llf):
+        return out
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        yhat, mse = gp.predict(Xc, eval_MSE=True)
+        yhat_only = gp.predict(Xc)
+    assert np.array_equal(yhat, yhat_only)
+    out.update(
+        sigma2=float(np.atleast_1d(gp.sigma2)[0]), noise_var=float(np.atleast_1d(gp.noise_var)[0]),
+        beta=np.asarray(gp.mean.beta, float).ravel(), gamma=gp.gamma.ravel(),
+        yhat=yhat.ravel(), mse=mse.ravel(), logdetL=float(np.log(np.diag(gp.C)).sum()),
+        rho2=float((gp.rho ** 2).sum()),
+    )
+    if ok:
+        out.update(G=np.asarray(gp.G), Ft=np.asarray(gp.Ft))
+    if keep_L:
+        out.update(L=gp.C)
+    pm = dict(minimize=minimize)
+    out.update(
+        ei=acq_rows(ns.EI, gp, Xc, **pm),
+        mgfi=acq_rows(ns.MGFI, gp, Xc, t=t, **pm),
+        mgfi_big_t=acq_rows(ns.MGFI, gp, Xc, t=30.0, **pm),  # exercises the 22.36 cap
+        epi=acq_rows(ns.EpsilonPI, gp, Xc, epsilon=eps, **pm),
+        t=t, alpha_ucb=alpha_ucb, eps=eps,
+    )
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out.update(ucb=np.asarray(ns.UCB(model=gp, alpha=alpha_ucb, **pm)(Xc)).ravel())
+    out.update(plugin=float(ns.EI(model=gp, **pm).plugin))
+    if with_grad:
+        par = np.asarray(theta, float) if mode == go.MODE_NOISELESS else np.r_[theta, sigma2_or_alpha]
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            l2, g = gp.log_likelihood_concentrated(par, eval_grad=True)
+        assert abs(l2 - llf) <= 1e-9 * abs(llf)
+        out.update(llf_grad=np.asarray(g, float).ravel())
+    if n_pg:
+        ydx, mdx = [], []
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            for x in Xc[:n_pg]:
+                a, b = gp.gradient(x)
+                ydx.append(a.ravel())
+                mdx.append(b.ravel())
+        out.update(y_dx=np.array(ydx), mse_dx=np.array(mdx))
+    return out
+
+
+def save(name, cases):
+    flat = {}
+    for cname, c in cases.items():
+        for k, v in c.items():
+            flat[f"{cname}/{k}"] = np.asarray(v)
+    path = os.path.join(HERE, name)
+    np.savez_compressed(path, **flat)
+    print(f"wrote {path}: {len(cases)} cases, {os.path.getsize(path)/1e3:.1f} kB")
+
+
+def appendix_b():
+    """SURVEY.md App. B closed-form inputs (no RNG)."""
+    X = np.sin(1 + np.arange(12).reshape(6, 2))
+    y = np.cos(np.arange(6))
+    Xc = 0.5 * np.cos(2 + np.arange(6).reshape(3, 2))
+    th = [0.7, 1.9]
+    cases = {
+        "rbf_ok": run_case(X, y, Xc, go.CORR_RBF, th, go.MODE_NOISY, True, 0.9, 1e-2, keep_L=True, eps=1e-10),
+        "m32_sk": run_case(X, y, Xc, go.CORR_MATERN32, th, go.MODE_NOISY, False, 0.9, 1e-2, keep_L=True, eps=1e-10),
+        "m52_ok": run_case(X, y, Xc, go.CORR_MATERN52, th, go.MODE_NOISY, True, 0.9, 1e-2, keep_L=True, eps=1e-10),
+    }
+    save("appendix_b.npz", cases)
+
+
+def medium():
+    """N=200, D=5: every kernel x estimation mode x OK/SK, minimise and maximise, llf gradients,
+    posterior gradients, near-duplicate candidates (EI / MGFI early-outs), linear trend."""
+    rng = np.random.default_rng(7)
+    N, D, M = 200, 5, 48
+    X = rng.uniform(-1, 2, (N, D))
+    y = np.sin(X).sum(axis=1) + 0.3 * rng.standard_normal(N)
+    y = (y - y.mean()) / y.std()
+    Xc = rng.uniform(-1, 2, (M, D))
+    Xc[:4] = X[:4]  # exact training points: s ~ 0 -> EI / MGFI early-outs
+    Xc[4:8] = X[4:8] + 1e-9
+    theta = np.array([0.3, 0.8, 0.15, 0.5, 1.1])
+    cases = {}
+    for corr, cn in [(go.CORR_RBF, "rbf"), (go.CORR_MATERN32, "m32"), (go.CORR_MATERN52, "m52"),
+                     (go.CORR_MATERN12, "m12"), (go.CORR_ABSEXP, "abs"), (go.CORR_CUBIC, "cub")]:
+        for mode, mn, last, nug in [(go.MODE_NOISELESS, "nl", None, None), (go.MODE_NOISY, "ny", 0.8, 1e-2),
+                                    (go.MODE_NOISE_ESTIM, "ne", 0.97, 1e-2)]:
+            for ok in (True, False):
+                grad = corr in (go.CORR_RBF, go.CORR_MATERN32, go.CORR_ABSEXP)
+                npg = 6 if corr in (go.CORR_RBF, go.CORR_MATERN32, go.CORR_ABSEXP) else 0
+                th = theta * (0.3 if corr == go.CORR_CUBIC else 1.0)
+                name = f"{cn}_{mn}_{'ok' if ok else 'sk'}"
+                cases[name] = run_case(X, y, Xc, corr, th, mode, ok, last, nug, beta=0.1,
+                                       with_grad=grad, n_pg=npg)
+                print(name, cases[name]["llf"])
+    cases["rbf_ny_ok_max"] = run_case(X, y, Xc, go.CORR_RBF, theta, go.MODE_NOISY, True, 0.8, 1e-2, minimize=False)
+    cases["m52_ny_ok_max"] = run_case(X, y, Xc, go.CORR_MATERN52, theta, go.MODE_NOISY, True, 0.8, 1e-2, minimize=False)
+    cases["rbf_iso_ny_ok"] = run_case(X, y, Xc, go.CORR_RBF, [0.4], go.MODE_NOISY, True, 0.8, 1e-6)
+    cases["rbf_ny_ok_lin"] = run_case(X, y, Xc, go.CORR_RBF, theta, go.MODE_NOISY, True, 0.8, 1e-2,
+                                      trend=go.TREND_LINEAR, n_pg=4)
+    cases["rbf_ny_sk_lin"] = run_case(X, y, Xc, go.CORR_RBF, theta, go.MODE_NOISY, False, 0.8, 1e-2,
+                                      trend=go.TREND_LINEAR, beta=np.linspace(-0.2, 0.3, D + 1))
+    # a rejected likelihood (llf > 0 -> -inf, gpr.py:981): tiny sigma2_total, smooth data
+    cases["rejected"] = run_case(X[:40], y[:40] * 1e-3, Xc, go.CORR_RBF, theta * 0.01, go.MODE_NOISY, True, 1e-5, 1e-8)
+    print("rejected llf:", cases["rejected"]["llf"])
+    save("medium.npz", cases)
+
+
+def canonical(big: bool):
+    """BASELINE.json config shapes with the canonical inputs of SURVEY.md §8d (inputs are regenerated from
+    the seeds in the tests; only outputs on the first 256 candidates of shard 0 are stored)."""
+    shapes = {
+        "C2": (1024, 8, go.CORR_RBF, 1e-6),
+        "C5": (2048, 64, go.CORR_RBF, 1e-6),
+        "C3": (4096, 16, go.CORR_MATERN52, 1e-6),
+    }
+    if big:
+        shapes["C4"] = (8192, 32, go.CORR_RBF, 1e-2)
+    cases = {}
+    for name, (N, D, corr, nug) in shapes.items():
+        X, y, theta = go.canonical_problem(N, D)
+        Xc = go.canonical_candidates(256, D)
+        c = run_case(X, y, Xc, corr, theta, go.MODE_NOISY, True, 1.0, nug)
+        for k in ("X", "y", "Xc", "Ft"):  # reproducible from seeds / large
+            c.pop(k, None)
+        c["N"], c["D"] = N, D
+        cases[name] = c
+        print(name, repr(c["llf"]))
+    save("canonical_big.npz" if big else "canonical.npz", cases)
+
+
+if __name__ == "__main__":
+    appendix_b()
+    medium()
+    canonical(False)
+    if "--big" in sys.argv:
+        canonical(True)
