@@ -1,0 +1,232 @@
+"""ctypes binding of libb200bo.so (include/b200bo.h).  There is NO CPU fallback: if the shared library
+is missing, or no sm_100a device is present, every compute entry point raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libb200bo.so")
+
+# ids, kept in sync with include/b200bo.h (tests/test_abi.py parses the header and compares)
+CORR_RBF, CORR_MATERN12, CORR_MATERN32, CORR_MATERN52, CORR_ABSEXP, CORR_CUBIC = range(6)
+MODE_NOISELESS, MODE_NOISY, MODE_NOISE_ESTIM = range(3)
+TREND_CONSTANT = 0
+FIT_OK, FIT_NOT_SPD, FIT_REJECTED = range(3)
+ACQ_EI, ACQ_PI, ACQ_UCB, ACQ_MGFI = range(4)
+HOST, DEVICE = 0, 1
+PREC_FP64, PREC_FAST = 0, 1
+STATE_L, STATE_LINV, STATE_GAMMA, STATE_YT, STATE_FT, STATE_RHO, STATE_BETA, STATE_G, STATE_R = range(9)
+N_TIMINGS = 8
+
+E_ARG, E_CUDA, E_STATE, E_NODEVICE = -1, -2, -3, -4
+
+
+class B200BOError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libb200bo error {code}: {msg}")
+        self.code = code
+
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+_lp = C.POINTER(C.c_int64)
+
+# name -> (restype, argtypes); every symbol include/b200bo.h declares
+SIGNATURES = {
+    "b200bo_last_error": (C.c_char_p, []),
+    "b200bo_version": (C.c_int, []),
+    "b200bo_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "b200bo_destroy": (C.c_int, [C.c_void_p]),
+    "b200bo_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "b200bo_set_precision": (C.c_int, [C.c_void_p, C.c_int]),
+    "b200bo_set_keep_R": (C.c_int, [C.c_void_p, C.c_int]),
+    "b200bo_set_train": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "b200bo_factor": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double,
+                                C.c_int, C.c_void_p, _dp, _dp, _dp, _ip]),
+    "b200bo_llf_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "b200bo_get_state": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
+    "b200bo_predict": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "b200bo_acq": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_double,
+                             C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b200bo_acq_from_moments": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int,
+                                          C.c_int, C.c_double, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                          C.c_void_p]),
+    "b200bo_get_timings": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "b200bo_get_fit_timings": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+}
+
+_lib = None
+
+
+def load_library():
+    """dlopen libb200bo.so and declare every prototype.  Raises if the library was not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `python -m bayesian_optimization_b200.build` "
+            "(there is no CPU fallback for the CUDA path)"
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise B200BOError(rc, load_library().b200bo_last_error().decode())
+
+
+def _f64(a, shape=None) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None:
+        a = a.reshape(shape)
+    return a
+
+
+def _ptr(a) -> int:
+    """host numpy array or (torch) device tensor -> raw address"""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    return int(a.data_ptr())
+
+
+class Engine:
+    """One engine = one b200bo handle = one fitted GP on one GPU."""
+
+    def __init__(self, device: int = 0):
+        self._lib = load_library()
+        h = C.c_void_p()
+        _check(self._lib.b200bo_create(int(device), C.byref(h)))
+        self._h = h
+        self.device = int(device)
+        self.N = self.D = 0
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.b200bo_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- configuration ---------------------------------------------------------------------------
+    def set_stream(self, cuda_stream_ptr: int):
+        _check(self._lib.b200bo_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    def set_precision(self, prec: int):
+        _check(self._lib.b200bo_set_precision(self._h, int(prec)))
+
+    def set_keep_R(self, keep: bool):
+        _check(self._lib.b200bo_set_keep_R(self._h, int(bool(keep))))
+
+    # ---- fit ---------------------------------------------------------------------------------------
+    def set_train(self, X: np.ndarray, y: np.ndarray):
+        X = _f64(X)
+        y = _f64(y).ravel()
+        if X.ndim != 2 or y.shape[0] != X.shape[0]:
+            raise ValueError("X must be (N, D) and y (N,)")
+        self.N, self.D = X.shape
+        _check(self._lib.b200bo_set_train(self._h, X.ctypes.data, y.ctypes.data, self.N, self.D))
+
+    def factor(self, corr: int, theta, mode: int, par_last: float = 0.0, noise_var: float = 0.0,
+               trend: int = TREND_CONSTANT, beta: Optional[Sequence[float]] = None):
+        """-> (llf, sigma2, noise_var, status)"""
+        theta = _f64(theta).ravel()
+        b = None if beta is None else _f64(beta).ravel()
+        llf, s2, nv, st = C.c_double(), C.c_double(), C.c_double(), C.c_int()
+        _check(self._lib.b200bo_factor(
+            self._h, int(corr), theta.ctypes.data, int(theta.size), int(mode), float(par_last), float(noise_var),
+            int(trend), None if b is None else b.ctypes.data, C.byref(llf), C.byref(s2), C.byref(nv), C.byref(st)))
+        return llf.value, s2.value, nv.value, st.value
+
+    def llf_grad(self, n_par: int) -> np.ndarray:
+        g = np.empty(n_par)
+        _check(self._lib.b200bo_llf_grad(self._h, g.ctypes.data, int(n_par)))
+        return g
+
+    def state(self, what: int) -> np.ndarray:
+        N = self.N
+        shape = {STATE_L: (N, N), STATE_LINV: (N, N), STATE_R: (N, N), STATE_BETA: (1,), STATE_G: (1,)}.get(what, (N,))
+        out = np.empty(shape)
+        _check(self._lib.b200bo_get_state(self._h, int(what), out.ctypes.data, out.size))
+        return out
+
+    # ---- predict / acquisition -------------------------------------------------------------------
+    def predict(self, Xc: np.ndarray, eval_mse: bool = True) -> Tuple[np.ndarray, Optional[np.ndarray]]:
+        Xc = _f64(Xc)
+        if Xc.ndim != 2 or Xc.shape[1] != self.D:
+            raise ValueError("Xc must be (M, D)")
+        M = Xc.shape[0]
+        yhat = np.empty(M)
+        mse = np.empty(M) if eval_mse else None
+        _check(self._lib.b200bo_predict(self._h, Xc.ctypes.data, M, HOST, int(eval_mse), yhat.ctypes.data,
+                                        None if mse is None else mse.ctypes.data))
+        return yhat, mse
+
+    def predict_device(self, Xc, yhat, mse=None):
+        """torch CUDA float64 tensors in/out (Xc (M,D) contiguous)."""
+        M = int(Xc.shape[0])
+        _check(self._lib.b200bo_predict(self._h, _ptr(Xc), M, DEVICE, int(mse is not None), _ptr(yhat), _ptr(mse)))
+
+    def acq(self, Xc, acq_id: int, minimize: bool, plugin: float, params, return_values: bool = False,
+            device_vals=None):
+        """Xc: host ndarray (M,D) or torch CUDA tensor.  -> (best_val (q,), best_idx (q,), vals (q,M) | None)"""
+        params = _f64(np.atleast_1d(params if params is not None else [0.0])).ravel()
+        q = int(params.size)
+        on_dev = not isinstance(Xc, np.ndarray)
+        if not on_dev:
+            Xc = _f64(Xc)
+        if Xc.ndim != 2 or Xc.shape[1] != self.D:
+            raise ValueError("Xc must be (M, D)")
+        M = int(Xc.shape[0])
+        best_val = np.empty(q)
+        best_idx = np.empty(q, dtype=np.int64)
+        vals = None
+        if on_dev:
+            vals = device_vals
+        elif return_values:
+            vals = np.empty((q, M))
+        _check(self._lib.b200bo_acq(self._h, _ptr(Xc), M, DEVICE if on_dev else HOST, int(acq_id), int(bool(minimize)),
+                                    float(plugin), params.ctypes.data, q, _ptr(vals), best_val.ctypes.data,
+                                    best_idx.ctypes.data))
+        return best_val, best_idx, vals
+
+    def acq_from_moments(self, yhat, mse, acq_id: int, minimize: bool, plugin: float, params,
+                         return_values: bool = True):
+        params = _f64(np.atleast_1d(params if params is not None else [0.0])).ravel()
+        q = int(params.size)
+        yhat = _f64(yhat).ravel()
+        mse = _f64(mse).ravel()
+        M = yhat.size
+        best_val = np.empty(q)
+        best_idx = np.empty(q, dtype=np.int64)
+        vals = np.empty((q, M)) if return_values else None
+        _check(self._lib.b200bo_acq_from_moments(self._h, yhat.ctypes.data, mse.ctypes.data, M, HOST, int(acq_id),
+                                                 int(bool(minimize)), float(plugin), params.ctypes.data, q,
+                                                 _ptr(vals), best_val.ctypes.data, best_idx.ctypes.data))
+        return best_val, best_idx, vals
+
+    def timings(self) -> np.ndarray:
+        t = np.zeros(N_TIMINGS)
+        _check(self._lib.b200bo_get_timings(self._h, t.ctypes.data, N_TIMINGS))
+        return t
+
+    def fit_timings(self) -> np.ndarray:
+        t = np.zeros(N_TIMINGS)
+        _check(self._lib.b200bo_get_fit_timings(self._h, t.ctypes.data, N_TIMINGS))
+        return t

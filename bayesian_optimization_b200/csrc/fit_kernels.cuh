@@ -1,0 +1,286 @@
+// fit_kernels.cuh -- device side of the fixed-hyper-parameter fit:
+//   kmat_assemble   R (N,N)                       gpr.py:772-782 (+ :935 / :952 / :966-967 per mode)
+//   chol_diag       64x64 diagonal factor + inverse (the POTF2 / TRTI2 leaves of the blocked algorithms)
+//   (panel / SYRK / TRTRI merges are launches of dgemm_kernel, see b200bo.cu)
+//   gemv kernels + scalar reductions   Yt, Ft, rho, gamma, log|L|, rho^T rho   gpr.py:795-811, :784-788
+// Paths are relative to /root/reference/bayes_optim/surrogate/gaussian_process/.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "gp_math.h"
+
+namespace b2 {
+
+constexpr int NB = 64;  // Cholesky / TRTRI block size
+constexpr size_t CHOL_DIAG_SMEM = 2 * NB * (NB + 1) * sizeof(double);
+
+// ---------------------------------------------------------------------------------------------------
+// Kernel-matrix assembly.  One CTA = one 64x64 tile (ti >= tj) of the lower triangle, mirrored into the
+// upper triangle through shared memory so both global writes are row-contiguous 16-byte stores.
+// Xt is the transposed training set (D x ld), so the loads are coalesced along the point index.
+// The pairwise-distance table of l1_cross_distances (gpr.py:48-61) is never materialised.
+//   off-diagonal: noiseless r | noisy (sigma2*r)/(sigma2+tau2) | noise_estim alpha*r
+//   diagonal    : 1           | (sigma2+tau2)/(sigma2+tau2)    | alpha + (1-alpha)
+//   rows/cols >= N (padding up to the tile multiple): identity.
+// ---------------------------------------------------------------------------------------------------
+struct AssembleArgs {
+  const double* Xt;  // (D, ld)
+  double* R;         // (ld, ld)
+  const double* theta;  // (D,)
+  int N, D, ld, corr, mode;
+  double sigma2, noise_var, alpha;
+};
+
+__global__ void __launch_bounds__(256) kmat_assemble_kernel(AssembleArgs p) {
+  // triangular tile index -> (ti, tj), ti >= tj
+  int t = blockIdx.x;
+  int ti = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+  while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+  while (ti * (ti + 1) / 2 > t) --ti;
+  int tj = t - ti * (ti + 1) / 2;
+  const int i0 = ti * NB, j0 = tj * NB;
+  extern __shared__ __align__(16) double sm[];
+  double* xi = sm;                    // [D][64]
+  double* xj = xi + p.D * NB;         // [D][64]
+  double* th = xj + p.D * NB;         // [D]
+  double* tile = th + ((p.D + 1) & ~1);  // [64][66]
+  const int tid = threadIdx.x;
+  for (int e = tid; e < p.D * NB; e += 256) {
+    int d = e / NB, c = e % NB;
+    xi[e] = p.Xt[(size_t)d * p.ld + i0 + c];
+    xj[e] = p.Xt[(size_t)d * p.ld + j0 + c];
+  }
+  for (int d = tid; d < p.D; d += 256) th[d] = p.theta[d];
+  __syncthreads();
+  // thread -> 4 rows x 4 cols (cols interleaved by 16 so smem reads of xj are conflict-free)
+  const int tr = (tid / 16) * 4, tc = tid % 16;
+  double acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = corr_init(p.corr);
+  for (int d = 0; d < p.D; ++d) {
+    double xa[4], xb[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) xa[a] = xi[d * NB + tr + a];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) xb[b] = xj[d * NB + tc + 16 * b];
+    double thd = th[d];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[a][b] = corr_accum(p.corr, acc[a][b], thd, xa[a] - xb[b]);
+  }
+  const double s2t = p.sigma2 + p.noise_var;
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      int gi = i0 + tr + a, gj = j0 + tc + 16 * b;
+      double v;
+      if (gi >= p.N || gj >= p.N) {
+        v = gi == gj ? 1.0 : 0.0;
+      } else if (gi == gj) {
+        v = p.mode == 1 ? (p.sigma2 * 1.0 + p.noise_var) / s2t : (p.mode == 2 ? p.alpha * 1.0 + (1.0 - p.alpha) : 1.0);
+      } else {
+        double r = corr_finish(p.corr, acc[a][b]);
+        v = p.mode == 1 ? (p.sigma2 * r) / s2t : (p.mode == 2 ? p.alpha * r : r);
+      }
+      tile[(tr + a) * 66 + tc + 16 * b] = v;
+    }
+  __syncthreads();
+  // lower tile: rows i0.., cols j0..  -- each thread stores 16-byte pairs, a warp covers one 512 B row
+  for (int e = tid; e < NB * NB / 2; e += 256) {
+    int r = e / (NB / 2), c = (e % (NB / 2)) * 2;
+    double2 v = make_double2(tile[r * 66 + c], tile[r * 66 + c + 1]);
+    *reinterpret_cast<double2*>(p.R + (size_t)(i0 + r) * p.ld + j0 + c) = v;
+  }
+  if (ti != tj) {  // mirrored tile: rows j0.., cols i0..
+    for (int e = tid; e < NB * NB / 2; e += 256) {
+      int r = e / (NB / 2), c = (e % (NB / 2)) * 2;
+      double2 v = make_double2(tile[c * 66 + r], tile[(c + 1) * 66 + r]);
+      *reinterpret_cast<double2*>(p.R + (size_t)(j0 + r) * p.ld + i0 + c) = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Diagonal block: factor A[jb,jb] = Ljj Ljj^T in shared memory, write Ljj back (lower; the strict upper
+// triangle of the block is zeroed) and its inverse to Dinv (64x64 row-major, zero strict upper).
+// status[0] |= 1 when a pivot is <= 0 or NaN (scipy.linalg.cholesky raises LinAlgError there, gpr.py:795).
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) chol_diag_kernel(double* __restrict__ A, int ld, double* __restrict__ Dinv,
+                                                        int* __restrict__ status) {
+  extern __shared__ __align__(16) double sm_cd[];
+  double(*s)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(sm_cd);
+  double(*x)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(sm_cd + NB * (NB + 1));  // inverse, x[r][c]
+  const int tid = threadIdx.x;
+  for (int e = tid; e < NB * NB; e += 256) {
+    int r = e / NB, c = e % NB;
+    s[r][c] = A[(size_t)r * ld + c];
+  }
+  __syncthreads();
+  for (int j = 0; j < NB; ++j) {
+    if (tid == 0) {
+      double d = s[j][j];
+      if (!(d > 0.0)) atomicOr(status, 1);
+      s[j][j] = sqrt(d);
+    }
+    __syncthreads();
+    const double djj = s[j][j];
+    if (tid > j && tid < NB) s[tid][j] /= djj;
+    __syncthreads();
+    for (int e = tid; e < NB * NB; e += 256) {
+      int r = e / NB, c = e % NB;
+      if (c > j && r >= c) s[r][c] -= s[r][j] * s[c][j];
+    }
+    __syncthreads();
+  }
+  // inverse by forward substitution, one column per thread: L x_c = e_c
+  if (tid < NB) {
+    const int c = tid;
+    for (int r = 0; r < c; ++r) x[r][c] = 0.0;
+    x[c][c] = 1.0 / s[c][c];
+    for (int r = c + 1; r < NB; ++r) {
+      double acc = 0.0;
+      for (int k = c; k < r; ++k) acc += s[r][k] * x[k][c];
+      x[r][c] = -acc / s[r][r];
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < NB * NB; e += 256) {
+    int r = e / NB, c = e % NB;
+    A[(size_t)r * ld + c] = c <= r ? s[r][c] : 0.0;
+    Dinv[e] = x[r][c];
+  }
+}
+
+// W[jb,jb] = Dinv[jb] for every diagonal block (level 0 of the recursive triangular inverse)
+__global__ void scatter_dinv_kernel(const double* __restrict__ Dinv, double* __restrict__ W, int ld) {
+  int jb = blockIdx.x;
+  for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
+    int r = e / NB, c = e % NB;
+    W[(size_t)(jb * NB + r) * ld + jb * NB + c] = Dinv[(size_t)jb * NB * NB + e];
+  }
+}
+
+// zero the strict upper triangle of a (ld x ld) matrix (the assembly wrote the symmetric R there)
+__global__ void zero_upper_kernel(double* __restrict__ A, int ld) {
+  size_t n = (size_t)ld * ld;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+    size_t r = e / ld, c = e % ld;
+    if (c > r) A[e] = 0.0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// y = W x (lower-triangular W, one warp per row, k <= row) for up to two right-hand sides at once:
+// Yt = L^-1 y (gpr.py:799) and Ft = L^-1 F (gpr.py:804; constant trend: F = 1 on real rows, 0 on padding).
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) tri_gemv2_kernel(const double* __restrict__ W, int ld, int n,
+                                                        const double* __restrict__ x0,
+                                                        const double* __restrict__ x1, double* __restrict__ y0,
+                                                        double* __restrict__ y1) {
+  int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const double* w = W + (size_t)row * ld;
+  double a0 = 0.0, a1 = 0.0;
+  for (int k = lane; k <= row; k += 32) {
+    double wv = w[k];
+    a0 += wv * x0[k];
+    a1 += wv * x1[k];
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+  }
+  if (lane == 0) {
+    y0[row] = a0;
+    y1[row] = a1;
+  }
+}
+
+// y = W^T x (gamma = L^-T rho, gpr.py:788): thread per column, rows j..n-1, coalesced across threads.
+// Rows are split over blockIdx.y in chunks, partial sums land in part[(chunk, col)] and are summed in a
+// fixed order by the caller's reduce kernel (deterministic).
+__global__ void __launch_bounds__(256) tri_gemvT_partial_kernel(const double* __restrict__ W, int ld, int n,
+                                                                const double* __restrict__ x,
+                                                                double* __restrict__ part, int rows_per_chunk) {
+  int col = blockIdx.x * blockDim.x + threadIdx.x;
+  int r0 = blockIdx.y * rows_per_chunk;
+  int r1 = min(n, r0 + rows_per_chunk);
+  if (col >= n) return;
+  double a = 0.0;
+  for (int r = max(r0, col); r < r1; ++r) a += W[(size_t)r * ld + col] * x[r];
+  part[(size_t)blockIdx.y * n + col] = a;
+}
+
+__global__ void colsum_partials_kernel(const double* __restrict__ part, int n, int chunks, double* __restrict__ y) {
+  int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= n) return;
+  double a = 0.0;
+  for (int c = 0; c < chunks; ++c) a += part[(size_t)c * n + col];
+  y[col] = a;
+}
+
+// Single-block deterministic reductions.  out[0] = sum Ft^2, out[1] = sum Ft*Yt, out[2] = sum log L_ii.
+__device__ __forceinline__ double block_sum_1024(double v, double* sh) {
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  double t = 0.0;
+  if (w == 0) {
+    t = lane < (int)(blockDim.x >> 5) ? sh[lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  }
+  return t;  // valid in warp 0
+}
+
+__global__ void __launch_bounds__(1024) fit_scalars_kernel(const double* __restrict__ L, int ld, int n,
+                                                           const double* __restrict__ Ft,
+                                                           const double* __restrict__ Yt, double* __restrict__ out) {
+  __shared__ double sh[32];
+  double ff = 0.0, fy = 0.0, ld_ = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    double f = Ft[i];
+    ff += f * f;
+    fy += f * Yt[i];
+    ld_ += log(L[(size_t)i * ld + i]);
+  }
+  double a = block_sum_1024(ff, sh);
+  double b = block_sum_1024(fy, sh);
+  double c = block_sum_1024(ld_, sh);
+  if (threadIdx.x == 0) {
+    out[0] = a;
+    out[1] = b;
+    out[2] = c;
+  }
+}
+
+// rho = Yt - coef * Ft  with coef = (Ft.Yt)/(Ft.Ft) (ordinary kriging: Q Q^T Yt, gpr.py:805-806) or the
+// fixed beta (simple kriging: L^-1 (F beta), gpr.py:808);  out[3] = rho^T rho, out[4] = coef used.
+__global__ void __launch_bounds__(1024) rho_kernel(const double* __restrict__ Yt, const double* __restrict__ Ft,
+                                                   int n, int estimate_trend, double beta_fixed,
+                                                   double* __restrict__ rho, double* __restrict__ out) {
+  __shared__ double sh[32];
+  double coef = estimate_trend ? out[1] / out[0] : beta_fixed;
+  double rr = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    double r = Yt[i] - coef * Ft[i];
+    rho[i] = r;
+    rr += r * r;
+  }
+  double a = block_sum_1024(rr, sh);
+  if (threadIdx.x == 0) {
+    out[3] = a;
+    out[4] = coef;
+  }
+}
+
+}  // namespace b2

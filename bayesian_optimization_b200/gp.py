@@ -1,0 +1,323 @@
+"""``GaussianProcess`` -- drop-in for ``bayes_optim.surrogate.GaussianProcess`` backed by libb200bo.so.
+
+Same constructor keywords, ``fit / predict / update`` signatures, attributes and error behaviour as the
+reference class (bayes_optim/surrogate/gaussian_process/gpr.py:78-1248); all arithmetic runs on the B200
+through the C ABI of include/b200bo.h.  There is no CPU path.
+
+Attribute map (reference -> here): ``X, y, theta_, sigma2, noise_var, gamma, C, Yt, Ft, G, Q, rho,
+mean.beta, is_fitted, log_likelihood_, par, estimation_mode`` -- the large ones (``C, gamma, Yt, Ft, rho,
+Q``) are fetched lazily from device memory.
+"""
+from __future__ import annotations
+
+import functools
+import warnings
+from typing import Optional
+
+import numpy as np
+from sklearn.utils import check_array, check_random_state, check_X_y
+
+from . import _lib
+from ._lib import Engine
+from .trend import BasisExpansionTrend, constant_trend
+
+_CORR_IDS = {
+    "squared_exponential": _lib.CORR_RBF,
+    "matern": _lib.CORR_MATERN32,  # the string API is nu = 1.5 only (kernel.py:159, gpr.py:206)
+    "matern12": _lib.CORR_MATERN12,
+    "matern32": _lib.CORR_MATERN32,
+    "matern52": _lib.CORR_MATERN52,
+    "absolute_exponential": _lib.CORR_ABSEXP,
+    "cubic": _lib.CORR_CUBIC,
+}
+_MODES = {"noiseless": _lib.MODE_NOISELESS, "noisy": _lib.MODE_NOISY, "noise_estim": _lib.MODE_NOISE_ESTIM}
+
+
+def resolve_corr(corr) -> int:
+    """Map the reference's ``corr`` argument (gpr.py:201-207, :1199-1208) to a device kernel id.  Callables
+    cannot run on the GPU; the one callable idiom the reference needs -- ``functools.partial(matern, nu=..)``,
+    the only route to Matern-5/2 -- is recognised by name."""
+    if isinstance(corr, str):
+        if corr in _CORR_IDS:
+            return _CORR_IDS[corr]
+        raise ValueError("corr should be one of %s or callable, %s was given." % (list(_CORR_IDS), corr))
+    if isinstance(corr, functools.partial) and getattr(corr.func, "__name__", "") == "matern":
+        nu = corr.keywords.get("nu", 1.5)
+        try:
+            return {0.5: _lib.CORR_MATERN12, 1.5: _lib.CORR_MATERN32, 2.5: _lib.CORR_MATERN52}[float(nu)]
+        except KeyError:
+            raise ValueError(f"matern nu={nu} has no device kernel (0.5, 1.5, 2.5 are available)") from None
+    name = getattr(corr, "__name__", None)
+    if name in _CORR_IDS:
+        return _CORR_IDS[name]
+    raise ValueError(f"corr={corr!r} is a callable without a device kernel")
+
+
+class GaussianProcess:
+    """The Gaussian Process model class (B200).  Keyword-compatible with gpr.py:211-228."""
+
+    _optimizer_types = ["BFGS", "CMA"]
+    _likelihood_functions = ["concentrated", "restricted"]
+
+    def __init__(self, mean=None, corr="squared_exponential", theta0=None, thetaL=None, thetaU=None, sigma2=None,
+                 nugget=1e-6, noise_estim=False, optimizer="BFGS", likelihood="concentrated", random_start=1,
+                 wait_iter=5, eval_budget=None, random_state=None, verbose=False, device: int = 0):
+        # gpr.py:229-277
+        self.mean = mean
+        self.corr = corr
+        self.sigma2 = sigma2
+        self.verbose = verbose
+        self.corr_type = corr
+        self.is_fitted = False
+        self.theta0 = np.array(theta0).flatten() if theta0 is not None else None
+        self.thetaL = np.array(thetaL).flatten()
+        self.thetaU = np.array(thetaU).flatten()
+        if not (np.isfinite(self.thetaL.astype(float)).all() and np.isfinite(self.thetaU.astype(float)).all()):
+            raise ValueError("all bounds are required finite.")
+        self.optimizer = optimizer
+        self.random_start = random_start
+        self.random_state = random_state
+        self.wait_iter = wait_iter
+        self.eval_budget = eval_budget
+        self.nugget = nugget
+        self.noise_var = np.atleast_1d(nugget) if nugget else 0
+        self.noise_estim = noise_estim
+        self.noisy = self.noise_var or self.noise_estim
+        if not self.noisy:
+            self.estimation_mode = "noiseless"
+        elif self.noise_estim:
+            self.estimation_mode = "noise_estim"
+        else:
+            self.estimation_mode = "noisy"
+        assert likelihood in self._likelihood_functions
+        self.likelihood = likelihood
+        if self.mean is None:
+            self.mean = constant_trend(len(self.thetaU), beta=0)  # simple kriging, gpr.py:269-270
+        if _is_basis_trend(self.mean):
+            self.mean_type = "basis_expansion"
+            self.estimate_trend = True if self.mean.beta is None else False
+        else:
+            raise ValueError("only BasisExpansionTrend means have a device implementation")
+        self.device = int(device)
+        self._engine: Optional[Engine] = None
+        self._cache = {}
+
+    # ---- engine plumbing ---------------------------------------------------------------------------
+    @property
+    def engine(self) -> Engine:
+        if self._engine is None:
+            self._engine = Engine(self.device)  # raises without libb200bo.so / a B200
+            if getattr(self, "X", None) is not None:
+                self._engine.set_train(self.X, self.y[:, 0])
+                if self.is_fitted:
+                    self._refactor()
+        return self._engine
+
+    def __getstate__(self):
+        # dill/pickle (BaseBO.save, base.py:499-519; joblib workers, bayes_opt.py:108-111): drop the device
+        # handle and the lazily fetched arrays; the deterministic factorisation is redone on first use.
+        st = self.__dict__.copy()
+        st["_engine"] = None
+        st["_cache"] = {}
+        return st
+
+    def __setstate__(self, st):
+        self.__dict__.update(st)
+
+    def get_params(self, deep=True):  # sklearn BaseEstimator surface used by clone()
+        keys = ["mean", "corr", "theta0", "thetaL", "thetaU", "sigma2", "nugget", "noise_estim", "optimizer",
+                "likelihood", "random_start", "wait_iter", "eval_budget", "random_state", "verbose"]
+        return {k: getattr(self, k if k != "corr" else "corr_type") for k in keys}
+
+    # ---- checks (gpr.py:279-310, :1199-1248) -------------------------------------------------------
+    def _check_params(self):
+        self._corr_id = resolve_corr(self.corr_type)
+        if self.thetaL is not None and self.thetaU is not None:
+            if self.thetaL.size != self.thetaU.size:
+                raise ValueError("thetaL and thetaU must have the same length.")
+            if self.theta0 is not None and self.theta0.size != self.thetaL.size:
+                raise ValueError("theta0, thetaL, and thetaU must have the same length.")
+            if np.any(self.thetaL <= 0) or np.any(self.thetaU < self.thetaL):
+                raise ValueError("The bounds must satisfy O < thetaL <= thetaU.")
+        self.verbose = bool(self.verbose)
+        if self.optimizer not in self._optimizer_types:
+            raise ValueError("optimizer should be one of %s" % self._optimizer_types)
+        self.random_start = int(self.random_start)
+
+    def _check_data(self, X, y):
+        X, y = check_X_y(X, y, multi_output=True, y_numeric=True)
+        if len(y.shape) == 1:
+            y = y.reshape(-1, 1)
+        if y.shape[1] != 1:
+            raise NotImplementedError("multi-target y is not implemented on device (SURVEY.md §8f rank 4)")
+        if not isinstance(self.mean, constant_trend) and type(self.mean).__name__ != "constant_trend":
+            raise NotImplementedError("only constant_trend has a device implementation (SURVEY.md §8f rank 4)")
+        self.X, self.y = np.ascontiguousarray(X, dtype=np.float64), np.ascontiguousarray(y, dtype=np.float64)
+        self._check_params()
+        self._cache = {}
+        self.engine.set_train(self.X, self.y[:, 0])
+        if self.estimate_trend:
+            self.F = self.mean.F(self.X)
+
+    # ---- likelihood at given hyper-parameters (gpr.py:920-991) -----------------------------------------
+    def _split_par(self, par):
+        par = np.asarray(par, dtype=np.float64).ravel()
+        if self.estimation_mode == "noiseless":
+            return par, 0.0
+        return par[:-1], float(par[-1])
+
+    def _beta_fixed(self):
+        return None if self.estimate_trend else np.asarray(self.mean.beta, dtype=np.float64).ravel()
+
+    def _factor(self, par):
+        theta, last = self._split_par(par)
+        nv = float(np.atleast_1d(self.noise_var)[0]) if self.estimation_mode == "noisy" else 0.0
+        llf, s2, nvo, status = self.engine.factor(self._corr_id, theta, _MODES[self.estimation_mode], last, nv,
+                                                  _lib.TREND_CONSTANT, self._beta_fixed())
+        self._cache = {}
+        return llf, s2, nvo, status
+
+    def log_likelihood_concentrated(self, par, env=None, eval_grad=False):
+        """Concentrated log-likelihood at ``par`` on the device; -inf when the factorisation fails or the
+        value is positive (gpr.py:981-982).  ``env`` receives sigma2 / noise_var like the reference's."""
+        llf, s2, nvo, status = self._factor(par)
+        n_par = np.size(par)
+        if status != _lib.FIT_OK:
+            return (-np.inf, np.zeros((n_par, 1))) if eval_grad else -np.inf
+        if env is not None:
+            env["sigma2"] = np.atleast_1d(s2)
+            env["noise_var"] = nvo
+        if eval_grad:
+            return llf, self.engine.llf_grad(n_par)
+        return llf
+
+    def _refactor(self):
+        par = self._par_vector()
+        _, _, _, status = self._factor(par)
+        if status != _lib.FIT_OK:  # pragma: no cover - the same inputs factored before
+            raise RuntimeError("re-factorisation of a fitted model failed")
+
+    def _par_vector(self):
+        if self.estimation_mode == "noiseless":
+            return np.asarray(self.theta_, dtype=np.float64)
+        return np.r_[np.asarray(self.theta_, dtype=np.float64), self._par_last]
+
+    # ---- fit -------------------------------------------------------------------------------------------
+    def fit_fixed(self, X, y, theta, par_last=None):
+        """Fit at GIVEN hyper-parameters: the reference's fit() with the optimiser loop removed, i.e.
+        ``_check_data`` (gpr.py:375-376) + the final likelihood evaluation (:1183-1188) + the attribute copy
+        and ``compute_beta_gamma`` (:402-415).  ``par_last`` = sigma2 ("noisy") or alpha ("noise_estim").
+        Returns the log-likelihood; the model is fitted iff it is finite."""
+        self.random_state = check_random_state(self.random_state)
+        self._check_data(X, y)
+        theta = np.asarray(theta, dtype=np.float64).ravel()
+        par = theta if self.estimation_mode == "noiseless" else np.r_[theta, float(par_last)]
+        env = {}
+        llf = self.log_likelihood_concentrated(par, env)
+        self.log_likelihood_ = llf
+        if not np.isfinite(llf):
+            self.is_fitted = False
+            return llf
+        self._adopt(theta, None if self.estimation_mode == "noiseless" else float(par_last), env)
+        return llf
+
+    def _adopt(self, theta, par_last, env):
+        self.theta_ = np.asarray(theta, dtype=np.float64)
+        self._par_last = par_last
+        self.noise_var = env["noise_var"]
+        self.sigma2 = env["sigma2"]
+        assert len(self.sigma2) == self.y.shape[1]
+        if self.estimate_trend:
+            self.mean.beta = self.engine.state(_lib.STATE_BETA)  # gpr.py:787
+        self.is_fitted = True
+
+    def fit(self, X, y):
+        """gpr.py:355-417.  Hyper-parameters by maximum likelihood on the device likelihood + gradient with the
+        reference's host L-BFGS-B restart loop; see ``hyperopt.optimize_hyperparameter``."""
+        from .hyperopt import optimize_hyperparameter
+
+        self.random_state = check_random_state(self.random_state)
+        self._check_data(X, y)
+        while True:
+            self.par, self.log_likelihood_, env = optimize_hyperparameter(self)
+            if np.isinf(self.log_likelihood_):
+                print("Invalid likelihood value. Increasing nugget...")  # gpr.py:390
+                if self.estimation_mode == "noiseless":
+                    self.estimation_mode = "noisy"
+                    self.noise_var = 1e-5
+                else:
+                    self.noise_var *= 10
+            else:
+                break
+        last = None
+        if "sigma2" in self.par:
+            last = float(self.par["sigma2"][0])
+        if "alpha" in self.par:
+            last = float(self.par["alpha"][0])
+        self._adopt(self.par["theta"], last, env)
+        return self
+
+    def update(self, X, y):
+        self.fit(X, y)  # gpr.py:419-422
+        return self
+
+    # ---- lazily fetched state ------------------------------------------------------------------------
+    def _state(self, key, what, shape=None):
+        if key not in self._cache:
+            a = self.engine.state(what)
+            self._cache[key] = a if shape is None else a.reshape(shape)
+        return self._cache[key]
+
+    @property
+    def C(self):
+        return self._state("C", _lib.STATE_L)
+
+    @property
+    def gamma(self):
+        return self._state("gamma", _lib.STATE_GAMMA, (-1, 1))
+
+    @property
+    def Yt(self):
+        return self._state("Yt", _lib.STATE_YT, (-1, 1))
+
+    @property
+    def rho(self):
+        return self._state("rho", _lib.STATE_RHO, (-1, 1))
+
+    @property
+    def Ft(self):
+        return self._state("Ft", _lib.STATE_FT, (-1, 1)) if self.estimate_trend else None
+
+    @property
+    def G(self):
+        return self._state("G", _lib.STATE_G, (1, 1)) if self.estimate_trend else None
+
+    @property
+    def Q(self):
+        return self.Ft / self.G[0, 0] if self.estimate_trend else None
+
+    # ---- predict (gpr.py:424-535) ----------------------------------------------------------------------
+    def predict(self, X, eval_MSE=False, batch_size=None):
+        assert hasattr(self, "X")
+        X = check_array(X)
+        n_features = self.X.shape[1]
+        self._check_params()
+        if X.shape[1] != n_features:
+            raise ValueError(
+                "The number of features in X (X.shape[1] = %d) should match the number of features used "
+                "for fit() which is %d." % (X.shape[1], n_features)
+            )
+        if batch_size is not None and (type(batch_size) is not int or batch_size <= 0):
+            raise Exception("batch_size must be a positive integer")
+        # batch_size only bounds host memory in the reference (and its branch is dead on Python 3,
+        # gpr.py:520); the engine streams candidates in SM-count-sized chunks regardless.
+        yhat, mse = self.engine.predict(X, eval_mse=bool(eval_MSE))
+        if eval_MSE:
+            return yhat.reshape(-1, 1), mse.reshape(-1, 1)
+        return yhat.reshape(-1, 1)
+
+
+def _is_basis_trend(mean) -> bool:
+    return isinstance(mean, BasisExpansionTrend) or any(
+        c.__name__ == "BasisExpansionTrend" for c in type(mean).__mro__
+    )

@@ -1,0 +1,70 @@
+"""Host-side mirror of the reference's trend (prior mean) classes for the part of them the hot path uses.
+
+Reference: bayes_optim/surrogate/gaussian_process/trend.py.  ``constant_trend`` (:69-91) is what ``fmin``
+and every upstream GP test use (bayes_optim/__init__.py:148, unittest/test_BO.py:34); ``beta=None`` means
+the coefficient is estimated (ordinary kriging), a number means simple kriging (gpr.py:269-275).
+The device implements the constant trend; the basis value F(x) = 1 is a literal inside the kernels.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+class BasisExpansionTrend:
+    """trend.py:10-64: ``m(X) = F(X) beta`` with ``beta`` stored as a (p, 1) column."""
+
+    def __init__(self, n_feature: int, n_dim: int, beta=None):
+        self.n_feature = int(n_feature)
+        self.n_dim = int(n_dim)
+        self.beta = beta
+
+    @property
+    def beta(self):
+        return self._beta
+
+    @beta.setter
+    def beta(self, beta):
+        # trend.py:21-29: scalars are broadcast to n_dim, everything is reshaped to a column
+        if beta is not None:
+            if not hasattr(beta, "__iter__"):
+                beta = np.array([beta] * self.n_dim)
+            beta = np.atleast_2d(beta).reshape(-1, 1)
+            if len(beta) != self.n_dim:
+                raise Exception("Shapes of beta and F do not match.")
+        self._beta = beta
+
+    def check_input(self, X):
+        # trend.py:51-58: a (D, M) input is silently transposed
+        X = np.atleast_2d(X)
+        if X.shape[1] != self.n_feature:
+            X = X.T
+        if X.shape[1] != self.n_feature:
+            raise Exception("X does not have the right size!")
+        return X
+
+    def __call__(self, X):
+        if self._beta is None:
+            raise Exception("beta is not set!")
+        return self.F(X).dot(self._beta)
+
+    def F(self, X):  # pragma: no cover - abstract
+        raise NotImplementedError
+
+
+class constant_trend(BasisExpansionTrend):
+    """trend.py:69-91: zero-order polynomial, p = 1, F(x) = 1."""
+
+    def __init__(self, n_feature: int, beta=None):
+        super().__init__(n_feature, 1, beta)
+
+    def F(self, X):
+        X = self.check_input(X)
+        return np.ones((X.shape[0], 1))
+
+    def Jacobian(self, x):
+        self.check_input(x)
+        return np.zeros((1, self.n_feature))
+
+    def Hessian(self, x):
+        self.check_input(x)
+        return np.zeros((self.n_feature, self.n_feature, self.n_dim))

@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py -- GP-predict + acquisition candidates/second on B200 (BASELINE.json metric).
+
+One "step" = one pass of the hot path over one batch of synthetic candidates: k* build, L^-1 k* contraction,
+posterior mean / variance, q acquisition criteria and their arg-max.  Default workload C3 (the config the
+metric is quoted on): N=4096, D=16, Matern-5/2 ARD, MGFI q=32, 1e7 candidates over 8 GPUs -> 1.25e6 candidates
+per GPU per step (weak scaling: per-GPU work fixed).  The fit (assembly + Cholesky + L^-1 + solves) runs once
+before the timed region and is reported in `config`.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C2|C3|C4|C5] [--impl reference]
+Under torchrun (N>1) every rank scores its own shard; the one exchange is a q-pair all-gather (NCCL).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "gp_predict_acq_candidates_per_sec"
+UNIT = "candidates/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="C3")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--m-per-gpu", type=int, default=0, help="override candidates per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="candidates in the CPU baseline sample")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks sampling during the timed region (B200_PROFILING.md recipe)
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.gpu)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's numpy/scipy path (the reference itself is pure Python and
+# cannot travel to the GPU box; oracle/gp_oracle.py restates it statement by statement)
+# --------------------------------------------------------------------------------------------------
+def cpu_chunk(N, D):
+    return max(64, min(8192, (512 << 20) // (N * D * 8)))  # chunk * N * D * 8 B <= 512 MB
+
+
+def cpu_fit(w):
+    from oracle import gp_oracle as go
+
+    X, y, theta = go.canonical_problem(w.N, w.D)
+    corr = go.CORR_NAMES[w.corr]
+    return go.fit_fixed(X, y, corr, theta, go.MODE_NOISY, sigma2=1.0, noise_var=w.nugget), go
+
+
+def cpu_step(ora, go, w, params, Xc):
+    """predict(eval_MSE=True) in chunks + q vectorised criteria + arg-max, like one GPU step"""
+    from bayesian_optimization_b200 import workloads as wl
+
+    yh, ms = go.predict_chunked(ora, Xc, cpu_chunk(w.N, w.D))
+    pl = go.plugin_value(ora.y, True)
+    acq = wl.ACQ_IDS[w.acq]
+    best = [int(np.argmax(go.acquisition(acq, yh, ms, ora.sigma2, pl, p, True))) for p in params]
+    return best
+
+
+def threads_used():
+    try:
+        from threadpoolctl import threadpool_info
+
+        return max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args, w, params):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from bayesian_optimization_b200 import workloads as wl
+
+    sample = args.cpu_sample or 4 * cpu_chunk(w.N, w.D)
+    ora, go = cpu_fit(w)
+    Xc = wl.canonical_candidates(sample, w.D)
+    for _ in range(args.warmup):
+        cpu_step(ora, go, w, params, Xc[: max(64, sample // 8)])
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_step(ora, go, w, params, Xc)
+    dt = time.perf_counter() - t0
+    val = sample * args.steps / dt
+    cores = threads_used()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": w.name, "describe": w.describe, "N": w.N, "D": w.D, "corr": w.corr, "acq": w.acq,
+                   "q": w.q, "candidates_per_step": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{sample} candidates/step (bounded sample of the {w.M_per_gpu}-candidate step), "
+                                   f"numpy/scipy oracle port of the reference, {cores} BLAS threads"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# B200 arm
+# --------------------------------------------------------------------------------------------------
+def run_b200(args, w, params):
+    import torch
+    import torch.distributed as dist
+
+    import bayesian_optimization_b200 as b2
+    from bayesian_optimization_b200 import sharded, workloads as wl
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    M = args.m_per_gpu or w.M_per_gpu
+    offset = rank * M
+    acq_id = wl.ACQ_IDS[w.acq]
+
+    # ---- fit once (replicated per rank, deterministic) -------------------------------------------
+    X, y, theta = wl.canonical_problem(w.N, w.D)
+    gp = b2.GaussianProcess(mean=b2.constant_trend(w.D), corr=w.corr, thetaL=[1e-5] * w.D, thetaU=[1e2] * w.D,
+                            nugget=w.nugget)
+    t0 = time.perf_counter()
+    llf = gp.fit_fixed(X, y, theta, 1.0)
+    fit_wall_ms = 1e3 * (time.perf_counter() - t0)
+    t0 = time.perf_counter()
+    gp.fit_fixed(X, y, theta, 1.0)
+    fit_wall_ms2 = 1e3 * (time.perf_counter() - t0)
+    fit_t = gp.engine.fit_timings()
+    eng = gp.engine
+    plugin = float(np.min(gp.y))
+
+    # ---- candidates: pinned host buffer (e2e) and a device-resident copy (value) ----------------------
+    xh = torch.empty((M, w.D), dtype=torch.float64, pin_memory=True)
+    wl.canonical_candidates(M, w.D, shard=rank, out=xh.numpy())
+    xd = xh.to(dev)
+    stream = torch.cuda.current_stream()
+    eng.set_stream(stream.cuda_stream)
+    torch.cuda.synchronize()
+
+    def step_device():
+        bv, bi, _ = eng.acq(xd, acq_id, True, plugin, params)
+        return sharded.global_argmax(bv, bi, offset, device=dev)
+
+    def step_e2e():
+        bv, bi, _ = eng.acq(xh.numpy(), acq_id, True, plugin, params)  # pinned host -> H2D inside, result D2H
+        return sharded.global_argmax(bv, bi, offset, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        kern = np.zeros(8)
+        out = None
+        for _ in range(steps):
+            out = fn()
+            kern += eng.timings()
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, kern, out
+
+    for _ in range(args.warmup):
+        step_device()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_dev, kern, best = timed(step_device, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    for _ in range(max(1, args.warmup // 3)):
+        step_e2e()
+    ms_e2e, _, best2 = timed(step_e2e, args.steps)
+    assert list(best[1]) == list(best2[1]), "device-resident and host-buffer paths disagree on the arg-max"
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    value = world * M * args.steps / (ms_dev * 1e-3)
+    e2e = world * M * args.steps / (ms_e2e * 1e-3)
+    # ---- roofline of the dominant kernel (the L^-1 k* contraction) -----------------------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    n_contract = kern[4]
+    launch_ms = kern[2] / max(n_contract, 1)
+    cand_per_launch = M * args.steps / max(n_contract, 1)
+    flops_per_cand = float(w.N) ** 2  # mul+add over the lower triangle of L^-1
+    achieved = cand_per_launch * flops_per_cand / (launch_ms * 1e-3) / 1e12
+    peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    roofline = {
+        "bound": "tensor", "kernel": "contract_fp64_kernel (fp64 DMMA: tcgen05 has no f64 kind)", "achieved": achieved,
+        "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+        "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s (of fallback)",
+        "traffic": None, "flops_per_candidate": flops_per_cand, "avg_launch_ms": launch_ms,
+        "candidates_per_launch": cand_per_launch, "share_of_step": kern[2] / max(kern[0], 1e-9),
+        "fp64_nominal_tflops": 40.0, "frac_of_fp64_nominal": achieved / 40.0,
+        "hbm_frac": value / world * (8 * w.D) / 1e9 / peaks.get("hbm_gbs", 6550.0),
+    }
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": w.name, "describe": w.describe, "N": w.N, "D": w.D, "corr": w.corr, "acq": w.acq,
+                   "q": w.q, "candidates_per_gpu_per_step": M, "candidates_per_step": world * M,
+                   "parallelism": f"candidate-shards x{world}", "precision": "fp64 DMMA parity path",
+                   "l2": "inputs_exceed_l2 (candidates + k* workspace > 126 MB per step)",
+                   "fit_ms_device": fit_t[0], "fit_ms_wall_first": fit_wall_ms, "fit_ms_wall": fit_wall_ms2,
+                   "fit_split_ms": {"assemble": fit_t[1], "cholesky": fit_t[2], "trtri": fit_t[3], "solves": fit_t[4]},
+                   "llf": llf, "argmax": [int(i) for i in best[1][:4]]},
+        "clocks": clocks,
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": M * w.D * 8, "d2h_bytes_per_step": 16 * w.q,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(kern[5]),
+        "kernel_ms_per_step": {"total_device": kern[0] / args.steps, "kstar": kern[1] / args.steps,
+                               "contract": kern[2] / args.steps, "acq_argmax": kern[3] / args.steps},
+        "roofline": roofline,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        sample = args.cpu_sample or 16 * cpu_chunk(w.N, w.D)
+        ora, go = cpu_fit(w)
+        Xc = wl.canonical_candidates(sample, w.D)
+        cpu_step(ora, go, w, params, Xc[: sample // 8])
+        t0 = time.perf_counter()
+        cb = cpu_step(ora, go, w, params, Xc)
+        dt = time.perf_counter() - t0
+        bv, bi, _ = eng.acq(Xc, acq_id, True, plugin, params)
+        cores = threads_used()
+        line["cpu_baseline"] = {
+            "value": sample / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{sample} of the {M} candidates of one step, oracle port of the reference's numpy/scipy path, "
+                      f"{cores} BLAS threads, {dt:.1f} s",
+            "argmax_matches_gpu": [int(i) for i in bi] == cb,
+        }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    from bayesian_optimization_b200 import workloads as wl
+
+    w = wl.WORKLOADS[args.workload]
+    params = wl.acquisition_params(w)
+    if args.impl == "reference":
+        run_reference(args, w, params)
+    else:
+        run_b200(args, w, params)
+
+
+if __name__ == "__main__":
+    main()

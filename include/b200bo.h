@@ -1,0 +1,152 @@
+/*
+ * b200bo.h -- C ABI of libb200bo.so: the B200 (sm_100a) GP-surrogate + acquisition engine.
+ *
+ * The reference (wangronin/Bayesian-Optimization, `bayes-optim` 0.3.0) is pure Python and has no FFI;
+ * its plug-in boundary for this path is duck-typing on `model.fit / model.predict(X, eval_MSE)` and the
+ * acquisition `__call__`.  Each entry point below names the reference interface it
+ * replaces (paths relative to /root/reference/bayes_optim/).  The Python mirror that binds these with
+ * ctypes is bayesian_optimization_b200/_lib.py; INTEGRATION.md shows the reference-side stub.
+ *
+ * Conventions: every function returns 0 on success or a negative B200BO_E_* code (no exceptions cross
+ * the ABI; b200bo_last_error() gives the message).  All matrices are row-major float64.  The caller owns
+ * every buffer.  One handle per (process, GPU); calls on one handle must be serialised by the caller.
+ * Calls are synchronous: they return after the results are in the caller's buffers.
+ */
+#ifndef B200BO_H
+#define B200BO_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200bo_ctx* b200bo_handle;
+
+/* error codes */
+#define B200BO_OK 0
+#define B200BO_E_ARG (-1)      /* bad argument (shape, id, NULL)                                     */
+#define B200BO_E_CUDA (-2)     /* CUDA runtime error; message in b200bo_last_error()                  */
+#define B200BO_E_STATE (-3)    /* call order: set_train -> factor -> predict/acq                      */
+#define B200BO_E_NODEVICE (-4) /* no CUDA device / wrong architecture (library is sm_100a only)       */
+
+/* correlation ids: surrogate/gaussian_process/gpr.py:201-207 (_correlation_types) + kernel.py */
+#define B200BO_CORR_RBF 0      /* "squared_exponential": exp(-sum theta d^2)        kernel.py:289-329 */
+#define B200BO_CORR_MATERN12 1 /* matern(nu=0.5): exp(-h), h = sqrt(sum theta d^2)  kernel.py:189-190 */
+#define B200BO_CORR_MATERN32 2 /* "matern" (nu=1.5): (1+sqrt3 h) exp(-sqrt3 h)      kernel.py:192-195 */
+#define B200BO_CORR_MATERN52 3 /* matern(nu=2.5): (1+sqrt5 h+5h^2/3) exp(-sqrt5 h)  kernel.py:197-200 */
+#define B200BO_CORR_ABSEXP 4   /* "absolute_exponential": exp(-sum theta |d|)       kernel.py:247-286 */
+#define B200BO_CORR_CUBIC 5    /* "cubic": prod (1 - 3 t^2 + 2 t^3), t=min(1,theta|d|) kernel.py:419-466 */
+
+/* estimation modes: gpr.py:258-263 */
+#define B200BO_MODE_NOISELESS 0   /* R = R0                      par = theta          gpr.py:932-947 */
+#define B200BO_MODE_NOISY 1       /* R = (s2 R0 + tau2 I)/(s2+tau2)  par = [theta, s2] gpr.py:963-979 */
+#define B200BO_MODE_NOISE_ESTIM 2 /* R = a R0 + (1-a) I          par = [theta, a]     gpr.py:949-961 */
+
+/* trend ids: surrogate/gaussian_process/trend.py */
+#define B200BO_TREND_CONSTANT 0 /* constant_trend, p = 1   trend.py:69-91 */
+
+/* factor status (out_status of b200bo_factor) */
+#define B200BO_FIT_OK 0
+#define B200BO_FIT_NOT_SPD 1  /* Cholesky pivot <= 0 or NaN: scipy raises LinAlgError -> llf = -inf (gpr.py:946,960,978) */
+#define B200BO_FIT_REJECTED 2 /* llf > 0 is rejected as -inf                                   (gpr.py:981-982)     */
+
+/* acquisition ids: acquisition/acquisition_fun.py */
+#define B200BO_ACQ_EI 0   /* EI          :150-189                               parameter unused      */
+#define B200BO_ACQ_PI 1   /* EpsilonPI / PI :192-235                            parameter = epsilon   */
+#define B200BO_ACQ_UCB 2  /* UCB         :107-147                               parameter = alpha     */
+#define B200BO_ACQ_MGFI 3 /* MGFI        :238-310                               parameter = t         */
+
+/* memory-location flags for candidate / output pointers */
+#define B200BO_HOST 0
+#define B200BO_DEVICE 1
+
+/* precision of the M-candidate predict path */
+#define B200BO_PREC_FP64 0 /* fp64 DMMA, parity path (default)                                          */
+#define B200BO_PREC_FAST 1 /* split-bf16 tcgen05 tensor-core pass + fp64 re-score of the arg-max band   */
+
+/* state ids for b200bo_get_state */
+#define B200BO_STATE_L 0     /* Cholesky factor "C"   (N,N) lower, zeros above   gpr.py:408, :795 */
+#define B200BO_STATE_LINV 1  /* L^-1                  (N,N) lower                (replaces solve_triangular gpr.py:494) */
+#define B200BO_STATE_GAMMA 2 /* gamma = L^-T rho      (N,)                       gpr.py:788 */
+#define B200BO_STATE_YT 3    /* Yt = L^-1 y           (N,)                       gpr.py:799 */
+#define B200BO_STATE_FT 4    /* Ft = L^-1 F           (N,p)                      gpr.py:804 */
+#define B200BO_STATE_RHO 5   /* rho                   (N,)                       gpr.py:806, :808 */
+#define B200BO_STATE_BETA 6  /* beta                  (p,)                       gpr.py:787 */
+#define B200BO_STATE_G 7     /* G of the thin QR of Ft (p,p)                     gpr.py:805 */
+#define B200BO_STATE_R 8     /* R as assembled, before factorisation (N,N)       gpr.py:772-782, :952, :966-967
+                                (only valid if b200bo_set_keep_R(h,1) was called before factor) */
+
+const char* b200bo_last_error(void);
+int b200bo_version(void);
+
+/* -- life cycle ---------------------------------------------------------------------------------------
+ * replaces GaussianProcess.__init__'s implicit host state (gpr.py:211-277): one engine per model. */
+int b200bo_create(int device, b200bo_handle* out);
+int b200bo_destroy(b200bo_handle h);
+/* run all kernels of this handle on an existing CUDA stream (cudaStream_t as void*), e.g. torch's */
+int b200bo_set_stream(b200bo_handle h, void* cuda_stream);
+int b200bo_set_precision(b200bo_handle h, int prec);
+int b200bo_set_keep_R(b200bo_handle h, int keep);
+
+/* -- training data: GaussianProcess._check_data (gpr.py:279-310) --------------------------------------
+ * X (N,D), y (N,) float64 host pointers.  The pairwise-distance pre-pass l1_cross_distances(X)
+ * (gpr.py:48-61) is never materialised: distances are recomputed inside the assembly kernel. */
+int b200bo_set_train(b200bo_handle h, const double* X, const double* y, int N, int D);
+
+/* -- fixed-hyper-parameter fit: log_likelihood_concentrated(par, env) (gpr.py:920-991) followed by the
+ * attribute copy and compute_beta_gamma of fit() (gpr.py:402-415, :784-788).
+ *   theta[n_theta]  n_theta == 1 (isotropic) or D
+ *   par_last        sigma2 (NOISY), alpha (NOISE_ESTIM), ignored (NOISELESS)
+ *   noise_var       tau^2 (NOISY only)
+ *   beta_or_null    NULL: ordinary kriging, beta estimated (mean.beta is None, gpr.py:273-275);
+ *                   else p fixed coefficients (simple kriging)
+ * outputs: llf (-inf when status != 0), sigma2, noise_var as env[] holds them. */
+int b200bo_factor(b200bo_handle h, int corr, const double* theta, int n_theta, int mode, double par_last,
+                  double noise_var, int trend, const double* beta_or_null, double* out_llf,
+                  double* out_sigma2, double* out_noise_var, int* out_status);
+
+/* analytic gradient of the likelihood at the last factor() point, as the reference computes it
+ * (gpr.py:994-1038, incl. its quirks g2/g3).  n_par = n_theta (+1 for NOISY / NOISE_ESTIM). */
+int b200bo_llf_grad(b200bo_handle h, double* out_grad, int n_par);
+
+int b200bo_get_state(b200bo_handle h, int what, double* out, size_t n_elems);
+
+/* -- GaussianProcess.predict(X, eval_MSE) (gpr.py:424-512) --------------------------------------------
+ * Xc (M,D); yhat (M,), mse (M,) (mse may be NULL when eval_mse == 0).  loc: B200BO_HOST / B200BO_DEVICE
+ * applies to Xc, yhat and mse alike. */
+int b200bo_predict(b200bo_handle h, const double* Xc, int64_t M, int loc, int eval_mse, double* yhat,
+                   double* mse);
+
+/* -- batched acquisition with the reference's per-row semantics + arg-max ------------------------------
+ * replaces AcquisitionFunction._predict + EI/EpsilonPI/PI/UCB/MGFI.__call__ (acquisition_fun.py:52-64,
+ * :127-137, :156-179, :209-218, :268-290) evaluated for q parameter values in ONE predict pass, and the
+ * candidate-set arg-max that stands in for argmax_restart (acquisition/optim/__init__.py:55-153).
+ *   plugin   already sign-adjusted f* as ImprovementBased.plugin stores it (acquisition_fun.py:96-104)
+ *   params   q values of (epsilon | alpha | t); ignored for EI (q criteria still reported)
+ *   vals     NULL or (q,M) criterion-major, same location as Xc
+ *   best_val (q,), best_idx (q,)  HOST pointers: max value and its LOWEST index (numpy argmax rule) */
+int b200bo_acq(b200bo_handle h, const double* Xc, int64_t M, int loc, int acq_id, int minimize,
+               double plugin, const double* params, int q, double* vals, double* best_val,
+               int64_t* best_idx);
+
+/* acquisition values from given (yhat, mse) -- the elementwise kernel alone (host or device pointers) */
+int b200bo_acq_from_moments(b200bo_handle h, const double* yhat, const double* mse, int64_t M, int loc,
+                            int acq_id, int minimize, double plugin, const double* params, int q,
+                            double* vals, double* best_val, int64_t* best_idx);
+
+/* -- instrumentation ------------------------------------------------------------------------------------
+ * CUDA-event timings (ms) of the last predict/acq call, recorded on the handle's stream:
+ *   [0] whole call on device  [1] k* build kernels  [2] L^-1 k* contraction kernels (the dominant kernel)
+ *   [3] acquisition + arg-max kernels  [4] number of contraction launches  [5] number of all launches
+ *   [6] fp64 re-scored candidates (FAST only) */
+#define B200BO_N_TIMINGS 8
+int b200bo_get_timings(b200bo_handle h, double* out, int n);
+/* timings (ms) of the last factor(): [0] total [1] assembly [2] cholesky [3] trtri [4] solves  [5] launches */
+int b200bo_get_fit_timings(b200bo_handle h, double* out, int n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200BO_H */
