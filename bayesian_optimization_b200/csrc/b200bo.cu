@@ -457,9 +457,58 @@ int b200bo_factor(b200bo_handle h, int corr, const double* theta, int n_theta, i
 }
 
 int b200bo_llf_grad(b200bo_handle h, double* out_grad, int n_par) {
-  (void)out_grad; (void)n_par;
-  CHECK_ARG(h, "handle is NULL");
-  return set_err(B200BO_E_STATE, "llf gradient is not implemented yet");
+  CHECK_ARG(h && out_grad, "NULL argument");
+  if (!h->factored) return set_err(B200BO_E_STATE, "llf_grad before a successful factor()");
+  const int N = h->N, D = h->D, ld = h->ld, nb = ld / NB, nt = h->n_theta;
+  CHECK_ARG(n_par == nt + (h->mode == B200BO_MODE_NOISELESS ? 0 : 1), "n_par does not match the estimation mode");
+  if (!corr_has_dtheta(h->corr))
+    return set_err(B200BO_E_ARG, "the reference leaves this kernel's theta-gradient unimplemented (gpr.py:758-768)");
+  CU_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  // Rinv = L^-T L^-1 (lower tiles): cho_solve((L, True), eye(N)) of gpr.py:997 as one TN GEMM on L^-1
+  GemmArgs g{};
+  g.A = h->W.p; g.B = h->W.p; g.C = h->S.p; g.lda = g.ldb = g.ldc = ld; g.K = ld; g.alpha = 1.0; g.beta = 0.0;
+  g.lower_only = 1; g.kb_mode = 2;  // W(k,i) = 0 for k < i: start at the row-tile offset (i >= j)
+  CU_TRY((launch_gemm<GemmTN, true, true>(h, g, ld, ld, 1)));
+  const int ntiles = nb * (nb + 1) / 2, S = D + 4;
+  CU_TRY(h->part.reserve((size_t)ntiles * S + S));
+  double s2t = h->sigma2 + h->noise_var;
+  GradArgs a;
+  a.Xt = h->Xt.p; a.theta = h->theta.p; a.Rinv = h->S.p; a.gamma = h->gamma.p; a.partial = h->part.p;
+  a.N = N; a.D = D; a.ld = ld; a.corr = h->corr;
+  if (h->mode == B200BO_MODE_NOISELESS) { a.a = 1.0 / h->sigma2; a.b = 1.0; }              // gpr.py:1002-1010
+  else if (h->mode == B200BO_MODE_NOISE_ESTIM) { a.a = h->par_last / s2t; a.b = h->par_last; }  // :1011-1019
+  else { a.a = 1.0 / s2t; a.b = 1.0; }                                                       // :1026-1038 (quirk g2)
+  size_t smem = ((size_t)2 * D * NB + ((D + 1) & ~1) + 2 * NB + 8 * S) * sizeof(double);
+  CU_TRY(cudaFuncSetAttribute(llf_grad_traces_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  llf_grad_traces_kernel<<<ntiles, 256, smem, st>>>(a);
+  CU_TRY(cudaGetLastError());
+  double* dout = h->part.p + (size_t)ntiles * S;
+  grad_reduce_kernel<<<S, 1024, 0, st>>>(h->part.p, ntiles, S, dout);
+  CU_TRY(cudaGetLastError());
+  std::vector<double> r(S);
+  CU_TRY(cudaMemcpyAsync(r.data(), dout, S * 8, cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  const double T1 = r[D], T2 = r[D + 1], trRinv = r[D + 2], gg = r[D + 3];
+  double last = 0.0;
+  if (h->mode == B200BO_MODE_NOISE_ESTIM) {
+    // -0.5 (sum(Rinv * (R0 - I)) - gamma^T (R0 - I) gamma / s2t): off-diagonal pairs only   gpr.py:1021-1025
+    last = -(T1 - T2 / s2t);
+  } else if (h->mode == B200BO_MODE_NOISY) {
+    // -0.5 (sum(Cinv * R0) - gamma_^T R0 gamma_), Cinv = Rinv / s2t, gamma_ = gamma / s2t    gpr.py:1027-1037
+    last = -0.5 * ((2.0 * T1 + trRinv) / s2t - (2.0 * T2 + gg) / (s2t * s2t));
+  }
+  if (nt == D) {
+    for (int d = 0; d < D; ++d) out_grad[d] = r[d];
+    if (n_par > nt) out_grad[nt] = last;
+  } else {
+    // Isotropic theta with D > 1.  The reference indexes its (N,N,D[+1]) gradient tensor with the PARAMETER
+    // index (gpr.py:1004-1005, :1034-1035), so parameter 0 sees only the feature-0 slice, and in "noisy" mode
+    // parameter 1 (sigma2) sees the feature-1 slice instead of R0.  Reproduced as is.
+    out_grad[0] = r[0];
+    if (n_par > 1) out_grad[1] = (h->mode == B200BO_MODE_NOISY && D > 1) ? r[1] : last;
+  }
+  return 0;
 }
 
 int b200bo_get_state(b200bo_handle h, int what, double* out, size_t n_elems) {

@@ -283,4 +283,132 @@ __global__ void __launch_bounds__(1024) rho_kernel(const double* __restrict__ Yt
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Likelihood-gradient traces (gpr.py:994-1038) without the (N,N,D) tensor of corr_grad_theta (gpr.py:745):
+// for every pair i > j the correlation, its theta-derivative factor and the coefficient
+//     c_ij = (a * gamma_i gamma_j - b * Rinv_ij) * dfactor_ij
+// are formed once in registers, then  out[d] = sum_{i>j} c_ij * w_d(x_i - x_j)  for all d.
+// Extra slots: [D] sum_{i>j} Rinv_ij R0_ij, [D+1] sum_{i>j} gamma_i gamma_j R0_ij, [D+2] trace(Rinv),
+// [D+3] gamma^T gamma  (the sigma2 / alpha components).  One CTA per 64x64 lower tile; per-tile partials are
+// summed in a fixed order by grad_reduce_kernel (deterministic).
+// ---------------------------------------------------------------------------------------------------
+struct GradArgs {
+  const double* Xt;     // (D, ld)
+  const double* theta;  // (D,)
+  const double* Rinv;   // (ld, ld), lower triangle valid
+  const double* gamma;  // (ld,)
+  double* partial;      // (ntiles, D + 4)
+  int N, D, ld, corr;
+  double a, b;
+};
+
+__global__ void __launch_bounds__(256) llf_grad_traces_kernel(GradArgs p) {
+  int t = blockIdx.x;
+  int ti = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+  while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+  while (ti * (ti + 1) / 2 > t) --ti;
+  int tj = t - ti * (ti + 1) / 2;
+  const int i0 = ti * NB, j0 = tj * NB;
+  extern __shared__ __align__(16) double sm[];
+  double* xi = sm;                       // [D][64]
+  double* xj = xi + p.D * NB;            // [D][64]
+  double* th = xj + p.D * NB;            // [D]
+  double* gi = th + ((p.D + 1) & ~1);    // [64]
+  double* gj = gi + NB;                  // [64]
+  double* wacc = gj + NB;                // [8][D+4]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int S = p.D + 4;
+  for (int e = tid; e < p.D * NB; e += 256) {
+    int d = e / NB, c = e % NB;
+    xi[e] = p.Xt[(size_t)d * p.ld + i0 + c];
+    xj[e] = p.Xt[(size_t)d * p.ld + j0 + c];
+  }
+  for (int d = tid; d < p.D; d += 256) th[d] = p.theta[d];
+  if (tid < NB) gi[tid] = p.gamma[i0 + tid];
+  else if (tid < 2 * NB) gj[tid - NB] = p.gamma[j0 + tid - NB];
+  for (int e = tid; e < 8 * S; e += 256) wacc[e] = 0.0;
+  __syncthreads();
+  const int tr = (tid / 16) * 4, tc = tid % 16;
+  double acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = corr_init(p.corr);
+  for (int d = 0; d < p.D; ++d) {
+    double xa[4], xb[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) xa[a] = xi[d * NB + tr + a];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) xb[b] = xj[d * NB + tc + 16 * b];
+    double thd = th[d];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[a][b] = corr_accum(p.corr, acc[a][b], thd, xa[a] - xb[b]);
+  }
+  double c[4][4];
+  double t1 = 0.0, t2 = 0.0, tr_ = 0.0, gg = 0.0;
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      int gi_ = i0 + tr + a, gj_ = j0 + tc + 16 * b;
+      bool live = gi_ > gj_ && gi_ < p.N;  // strict lower triangle of the real matrix
+      double rinv = p.Rinv[(size_t)gi_ * p.ld + gj_];
+      if (live) {
+        double r0 = corr_finish(p.corr, acc[a][b]);
+        double g2 = gi[tr + a] * gj[tc + 16 * b];
+        c[a][b] = (p.a * g2 - p.b * rinv) * corr_dtheta_factor(p.corr, acc[a][b]);
+        t1 += rinv * r0;
+        t2 += g2 * r0;
+      } else {
+        c[a][b] = 0.0;
+        if (gi_ == gj_ && gi_ < p.N) {
+          tr_ += rinv;
+          gg += gi[tr + a] * gi[tr + a];
+        }
+      }
+    }
+  auto warp_add = [&](double v, int slot) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) wacc[warp * S + slot] += v;
+  };
+  for (int d = 0; d < p.D; ++d) {
+    double xa[4], xb[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) xa[a] = xi[d * NB + tr + a];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) xb[b] = xj[d * NB + tc + 16 * b];
+    double pd = 0.0;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) pd += c[a][b] * corr_dtheta_weight(p.corr, xa[a] - xb[b]);
+    warp_add(pd, d);
+  }
+  warp_add(t1, p.D);
+  warp_add(t2, p.D + 1);
+  warp_add(tr_, p.D + 2);
+  warp_add(gg, p.D + 3);
+  __syncthreads();
+  for (int sidx = tid; sidx < S; sidx += 256) {
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += wacc[w * S + sidx];
+    p.partial[(size_t)t * S + sidx] = v;
+  }
+}
+
+// out[s] = sum over tiles of partial[tile][s], fixed order; one block per slot
+__global__ void __launch_bounds__(1024) grad_reduce_kernel(const double* __restrict__ partial, int ntiles, int S,
+                                                           double* __restrict__ out) {
+  __shared__ double sh[32];
+  int s = blockIdx.x;
+  double v = 0.0;
+  for (int t = threadIdx.x; t < ntiles; t += blockDim.x) v += partial[(size_t)t * S + s];
+  double a = block_sum_1024(v, sh);
+  if (threadIdx.x == 0) out[s] = a;
+}
+
 }  // namespace b2

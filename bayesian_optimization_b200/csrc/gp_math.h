@@ -50,6 +50,29 @@ B2_HD double corr_finish(int corr, double acc) {
   }
 }
 
+// ---- d r / d theta_j = corr_dtheta_factor(acc) * corr_dtheta_weight(diff_j) -------------------------------
+// The reference's corr_grad_theta (surrogate/gaussian_process/gpr.py:736-770) implements RBF (:748:
+// -diff^2 R), Matern-3/2 (:757: -3 exp(-sqrt3 h) diff^2 / 2) and absolute_exponential (:761: -|diff| R) and
+// leaves the rest unbound (fit() crashes upstream).  Matern-5/2 is provided here from its
+// derivative  d/ds[(1+k+k^2/3)e^-k] = -(5/6)(1+k)e^-k,  k = sqrt(5 s),  s = sum theta_j d_j^2.
+B2_HD bool corr_has_dtheta(int corr) { return corr == RBF || corr == MATERN32 || corr == MATERN52 || corr == ABSEXP; }
+B2_HD double corr_dtheta_factor(int corr, double acc) {
+  switch (corr) {
+    case RBF:
+    case ABSEXP:
+      return -exp(-acc);
+    case MATERN32:
+      return -1.5 * exp(-sqrt(acc) * 1.7320508075688772);
+    case MATERN52: {
+      double k = sqrt(acc) * 2.23606797749979;
+      return -(5.0 / 6.0) * (1.0 + k) * exp(-k);
+    }
+    default:
+      return 0.0;
+  }
+}
+B2_HD double corr_dtheta_weight(int corr, double diff) { return corr == ABSEXP ? fabs(diff) : diff * diff; }
+
 // ---- normal distribution ----------------------------------------------------------------------------
 // scipy.stats.norm.cdf -> special.ndtr (erfc based); norm.pdf = exp(-x^2/2)/sqrt(2 pi)
 B2_HD double norm_cdf(double z) { return 0.5 * erfc(-z * 0.7071067811865476); }

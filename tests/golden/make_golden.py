@@ -196,9 +196,43 @@ def canonical(big: bool):
     save("canonical_big.npz" if big else "canonical.npz", cases)
 
 
+def fit_full():
+    """Full reference fit() (L-BFGS-B on the likelihood, global numpy RNG seeded) on small problems:
+    pins the final likelihood / hyper-parameters the device fit loop has to reach."""
+    cases = {}
+    rng = np.random.default_rng(11)
+    for name, N, D, corr, mode in [("rbf_ny", 120, 3, go.CORR_RBF, go.MODE_NOISY),
+                                   ("m32_ny", 150, 4, go.CORR_MATERN32, go.MODE_NOISY),
+                                   ("rbf_ne", 100, 2, go.CORR_RBF, go.MODE_NOISE_ESTIM),
+                                   ("rbf_nl", 80, 2, go.CORR_RBF, go.MODE_NOISELESS)]:
+        X = rng.uniform(0, 1, (N, D))
+        y = np.sin(5 * X).sum(axis=1) + 0.2 * rng.standard_normal(N)
+        y = (y - y.mean()) / y.std()
+        Xc = rng.uniform(0, 1, (32, D))
+        gp = make_gp(corr, D, mode, True, 1e-2)
+        gp.thetaL, gp.thetaU = np.full(D, 1e-2), np.full(D, 1e2)
+        gp.theta0 = np.full(D, 1.0)
+        gp.random_start = 2
+        np.random.seed(5)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            gp.fit(X, y)
+            yhat, mse = gp.predict(Xc, eval_MSE=True)
+        cases[name] = dict(X=X, y=y, Xc=Xc, corr=corr, mode=mode, theta=gp.theta_, llf=gp.log_likelihood_,
+                           sigma2=np.atleast_1d(gp.sigma2)[0], noise_var=np.atleast_1d(gp.noise_var)[0],
+                           eval_count=gp.eval_count, yhat=yhat.ravel(), mse=mse.ravel(),
+                           beta=np.asarray(gp.mean.beta).ravel())
+        print(name, gp.theta_, gp.log_likelihood_, gp.eval_count)
+    save("fit_full.npz", cases)
+
+
 if __name__ == "__main__":
+    if "--fit-only" in sys.argv:
+        fit_full()
+        sys.exit(0)
     appendix_b()
     medium()
     canonical(False)
+    fit_full()
     if "--big" in sys.argv:
         canonical(True)

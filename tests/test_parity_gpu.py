@@ -146,7 +146,7 @@ def test_fresh_inputs_vs_oracle_and_ragged_shapes():
     # M larger than one device chunk (148 * 128 = 18944): chunk seams must be invisible
     N, D, M = 200, 4, 40001
     X = rng.uniform(0, 1, (N, D))
-    y = np.cos(3 * X).sum(axis=1)
+    y = np.cos(3 * X).sum(axis=1) + 0.3 * rng.standard_normal(N)
     theta = np.full(D, 2.0)
     Xc = rng.uniform(0, 1, (M, D))
     ora = go.fit_fixed(X, y, go.CORR_MATERN52, theta, go.MODE_NOISY, sigma2=0.7, noise_var=1e-4)
@@ -154,7 +154,7 @@ def test_fresh_inputs_vs_oracle_and_ragged_shapes():
     import functools
     gp = b2.GaussianProcess(mean=b2.constant_trend(D), corr=functools.partial(matern, nu=2.5), thetaL=[1e-5] * D,
                             thetaU=[1e2] * D, nugget=1e-4)
-    gp.fit_fixed(X, y, theta, 0.7)
+    assert gp.fit_fixed(X, y, theta, 0.7) == pytest.approx(ora.llf, rel=1e-10)
     yo, mo = go.predict_chunked(ora, Xc, 4096)
     yd, md = gp.predict(Xc, eval_MSE=True)
     np.testing.assert_allclose(yd, yo, rtol=1e-9, atol=1e-9)
