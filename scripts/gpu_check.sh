@@ -19,8 +19,10 @@ tail -c 3000 $OUT/bench.json; tail -5 $OUT/bench.err
 echo "== bench C2"; timeout 600 python bench.py --workload C2 --steps 3 --warmup 3 > $OUT/bench_C2.json 2> $OUT/bench_C2.err; echo "bench C2 rc=$?"
 tail -c 1500 $OUT/bench_C2.json
 echo "== ncu launch list"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv \
-  python bench.py --steps 1 --warmup 3 --m-per-gpu 37888 --no-cpu-baseline > $OUT/ncu_launch_bench.log 2>&1; echo "ncu list rc=$?"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_fit.csv \
+  python bench.py --steps 1 --warmup 3 --m-per-gpu 18944 --no-cpu-baseline > /dev/null 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"kstar|contract|acq_kernel|argmax|mse_kernel" -c 200 --csv --log-file $OUT/launches.csv \
+  python bench.py --steps 2 --warmup 3 --m-per-gpu 75776 --no-cpu-baseline > $OUT/ncu_launch_bench.log 2>&1; echo "ncu list rc=$?"
 echo "== ncu full (contract kernel)"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:contract -s 2 -c 1 -o $OUT/prof_contract \
   python bench.py --steps 1 --warmup 3 --m-per-gpu 18944 --no-cpu-baseline > $OUT/ncu_full.log 2>&1; echo "ncu full rc=$?"
