@@ -55,6 +55,8 @@ SIGNATURES = {
     "b200bo_acq_from_moments": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int,
                                           C.c_int, C.c_double, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                           C.c_void_p]),
+    "b200bo_debug_fast_rt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p]),
     "b200bo_get_timings": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "b200bo_get_fit_timings": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
 }
@@ -220,6 +222,16 @@ class Engine:
                                                  int(bool(minimize)), float(plugin), params.ctypes.data, q,
                                                  _ptr(vals), best_val.ctypes.data, best_idx.ctypes.data))
         return best_val, best_idx, vals
+
+    def debug_fast_rt(self, Xc: np.ndarray):
+        """test hook: (rt (M,N) float32, yhat, sum rt^2, Ft^T rt) exactly as the tensor-core kernel produced them"""
+        Xc = _f64(Xc)
+        M = Xc.shape[0]
+        rt = np.empty((M, self.N), dtype=np.float32)
+        yh, ss, df = np.empty(M), np.empty(M), np.empty(M)
+        _check(self._lib.b200bo_debug_fast_rt(self._h, Xc.ctypes.data, M, rt.ctypes.data, yh.ctypes.data,
+                                              ss.ctypes.data, df.ctypes.data))
+        return rt, yh, ss, df
 
     def timings(self) -> np.ndarray:
         t = np.zeros(N_TIMINGS)

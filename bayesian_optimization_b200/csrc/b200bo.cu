@@ -1,6 +1,8 @@
 // b200bo.cu -- host driver + C ABI (include/b200bo.h) of the B200 GP-surrogate / acquisition engine.
 // sm_100a only.  No CPU fallback: every entry point fails with B200BO_E_NODEVICE / B200BO_E_CUDA when the
 // device is missing.
+#include <cuda.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
@@ -12,6 +14,7 @@
 
 #include "../../include/b200bo.h"
 #include "dgemm.cuh"
+#include "fast_kernels.cuh"
 #include "fit_kernels.cuh"
 #include "predict_kernels.cuh"
 
@@ -105,6 +108,19 @@ struct b200bo_ctx {
   int Mc = 0;
   DevBuf<double> Xc, Kst, yhat, sumsq, dotf, mse, params, part_val, best_val, vals;
   DevBuf<long long> part_idx, best_idx;
+  // tensor-core (B200BO_PREC_FAST) state, built lazily after factor()
+  bool fast_ready = false, calibrated = false;
+  int DP = 0, b_scale_log2 = 0;
+  double dy_cal = 0, ds_cal = 0;
+  DevBuf<__half> Lh, Ll;
+  DevBuf<float> Xs, band_hi, dbg_w;
+  DevBuf<double> cscale, fvec, f_yhat, f_sumsq, f_dotf, stage[2], thr, thr_part, Xband, errout;
+  DevBuf<long long> band_list;
+  DevBuf<int> band_count, err_flag;
+  CUtensorMap map_hi, map_lo;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_used[2] = {nullptr, nullptr};
+  bool want_dbg_w = false;
   EvPool evs;
   double timings[B200BO_N_TIMINGS] = {0};
   double fit_timings[B200BO_N_TIMINGS] = {0};
@@ -209,6 +225,15 @@ int b200bo_destroy(b200bo_handle h) {
   h->Xc.release(); h->Kst.release(); h->yhat.release(); h->sumsq.release(); h->dotf.release();
   h->mse.release(); h->params.release(); h->part_val.release(); h->best_val.release(); h->vals.release();
   h->part_idx.release(); h->best_idx.release();
+  h->Lh.release(); h->Ll.release(); h->Xs.release(); h->band_hi.release(); h->dbg_w.release();
+  h->cscale.release(); h->fvec.release(); h->f_yhat.release(); h->f_sumsq.release(); h->f_dotf.release();
+  h->stage[0].release(); h->stage[1].release(); h->thr.release(); h->thr_part.release(); h->Xband.release();
+  h->errout.release(); h->band_list.release(); h->band_count.release(); h->err_flag.release();
+  for (int i = 0; i < 2; ++i) {
+    if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
+    if (h->ev_used[i]) cudaEventDestroy(h->ev_used[i]);
+  }
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   h->evs.destroy();
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -227,7 +252,7 @@ int b200bo_set_stream(b200bo_handle h, void* s) {
 
 int b200bo_set_precision(b200bo_handle h, int prec) {
   CHECK_ARG(h, "handle is NULL");
-  CHECK_ARG(prec == B200BO_PREC_FP64, "only B200BO_PREC_FP64 is available in this build");
+  CHECK_ARG(prec == B200BO_PREC_FP64 || prec == B200BO_PREC_FAST, "unknown precision id");
   h->prec = prec;
   return 0;
 }
@@ -280,6 +305,8 @@ int b200bo_factor(b200bo_handle h, int corr, const double* theta, int n_theta, i
   const int N = h->N, D = h->D, ld = h->ld, nb = ld / NB;
   const size_t nn = (size_t)ld * ld;
   h->factored = false;
+  h->fast_ready = false;
+  h->calibrated = false;
   CU_TRY(h->A.reserve(nn));
   CU_TRY(h->W.reserve(nn));
   CU_TRY(h->S.reserve(nn));
@@ -549,24 +576,18 @@ int b200bo_get_state(b200bo_handle h, int what, double* out, size_t n_elems) {
   return set_err(B200BO_E_ARG, "unknown state id");
 }
 
-// Shared driver of predict / acq.  acq_id < 0: predict only.
-static int run_candidates(b200bo_handle h, const double* Xc, int64_t M, int loc, int eval_mse, double* yhat_out,
-                          double* mse_out, int acq_id, int minimize, double plugin, const double* params, int q,
-                          double* vals, double* best_val, int64_t* best_idx) {
-  CHECK_ARG(h, "handle is NULL");
-  if (!h->factored) return set_err(B200BO_E_STATE, "predict before a successful factor()");
-  CHECK_ARG(M >= 0, "M < 0");
-  CHECK_ARG(loc == B200BO_HOST || loc == B200BO_DEVICE, "bad loc");
-  CU_TRY(cudaSetDevice(h->device));
-  const bool do_acq = acq_id >= 0;
-  const bool dev = loc == B200BO_DEVICE;
-  int rc = ensure_predict_ws(h, q, do_acq && vals && !dev);
-  if (rc) return rc;
+// ------------------------------------------------------------------------------------------------------
+// fp64 building block: moments of m <= Mc device-resident candidates -> yh (m), h->sumsq, h->dotf
+// ------------------------------------------------------------------------------------------------------
+struct LaunchCount {
+  int all = 0, contract = 0;
+};
+
+static int fp64_moments(b200bo_handle h, const double* xc_dev, int m, double* yh, int eval_mse, PhaseTimer* pt,
+                        LaunchCount* lc) {
   cudaStream_t st = h->stream;
-  const int D = h->D, ld = h->ld, Mc = h->Mc;
-  h->evs.reset();
-  PhaseTimer pt{h};
-  int launches = 0, contract_launches = 0;
+  const int D = h->D, ld = h->ld;
+  const int mpad = round_up(m, PC_BM);
   static bool attr_done = false;
   if (!attr_done) {
     CU_TRY(cudaFuncSetAttribute(contract_fp64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PredCore::SMEM_BYTES));
@@ -575,68 +596,110 @@ static int run_candidates(b200bo_handle h, const double* Xc, int64_t M, int loc,
   const size_t ks_smem = ((size_t)KS_ROWS * D + D) * sizeof(double);
   if (ks_smem > 48 * 1024)
     CU_TRY(cudaFuncSetAttribute(kstar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ks_smem));
-  if (do_acq) {
-    std::vector<double> pr(q);
-    for (int c = 0; c < q; ++c) pr[c] = params ? params[c] : 0.0;
-    CU_TRY(cudaMemcpyAsync(h->params.p, pr.data(), q * 8, cudaMemcpyHostToDevice, st));
-    std::vector<long long> bi(q, -1);
-    CU_TRY(cudaMemsetAsync(h->best_val.p, 0, q * 8, st));
-    CU_TRY(cudaMemcpyAsync(h->best_idx.p, bi.data(), q * 8, cudaMemcpyHostToDevice, st));
-    CU_TRY(cudaStreamSynchronize(st));  // pr / bi are stack-owned
+  if (pt) pt->begin(0);
+  KstarArgs k;
+  k.Xc = xc_dev; k.Xt = h->Xt.p; k.theta = h->theta.p; k.gamma = h->gamma.p;
+  k.Kst = eval_mse ? h->Kst.p : nullptr; k.yhat = yh;
+  k.M = m; k.N = h->N; k.D = D; k.ld = ld; k.corr = h->corr; k.beta = h->beta;
+  kstar_kernel<<<mpad / KS_ROWS, 256, ks_smem, st>>>(k);
+  CU_TRY(cudaGetLastError());
+  ++lc->all;
+  if (pt) pt->end(0);
+  if (eval_mse) {
+    if (pt) pt->begin(1);
+    ContractArgs c;
+    c.Kst = h->Kst.p; c.Linv = h->W.p; c.Ft = h->Ft.p; c.sumsq = h->sumsq.p; c.dotf = h->dotf.p; c.ld = ld;
+    contract_fp64_kernel<<<mpad / PC_BM, PredCore::NT, PredCore::SMEM_BYTES, st>>>(c);
+    CU_TRY(cudaGetLastError());
+    ++lc->all;
+    ++lc->contract;
+    if (pt) pt->end(1);
   }
+  return 0;
+}
+
+// acquisition + arg-max of m candidates whose moments are in (yh, h->sumsq, h->dotf); merges into h->best_*
+static int acq_stage(b200bo_handle h, const double* yh, int m, long long idx_base, const long long* idx_map,
+                     int acq_id, int minimize, double plugin, int q, double* vals, long long vals_ld,
+                     long long vals_off, double* mse_out, LaunchCount* lc) {
+  cudaStream_t st = h->stream;
+  AcqArgs g{};
+  g.yhat = yh; g.sumsq = h->sumsq.p; g.dotf = h->dotf.p; g.mse_in = nullptr; g.mse_out = mse_out;
+  g.M = m; g.estimate_trend = h->estimate_trend; g.sigma2 = h->sigma2; g.G = h->G;
+  g.idx_base = idx_base; g.idx_map = idx_map;
+  g.vals = vals; g.vals_ld = vals_ld; g.vals_off = vals_off;
+  g.params = h->params.p; g.part_val = h->part_val.p; g.part_idx = h->part_idx.p;
+  g.acq = acq_id; g.minimize = minimize; g.q = q; g.plugin = plugin;
+  int nblk = std::min(h->num_sms, (m + 255) / 256);
+  acq_kernel<<<dim3(nblk, q), 256, 0, st>>>(g);
+  CU_TRY(cudaGetLastError());
+  argmax_merge_kernel<<<(q + 63) / 64, 64, 0, st>>>(h->part_val.p, h->part_idx.p, nblk, q, h->best_val.p, h->best_idx.p);
+  CU_TRY(cudaGetLastError());
+  lc->all += 2;
+  return 0;
+}
+
+static int upload_params_reset_best(b200bo_handle h, const double* params, int q) {
+  cudaStream_t st = h->stream;
+  std::vector<double> pr(q);
+  for (int c = 0; c < q; ++c) pr[c] = params ? params[c] : 0.0;
+  CU_TRY(cudaMemcpyAsync(h->params.p, pr.data(), q * 8, cudaMemcpyHostToDevice, st));
+  std::vector<long long> bi(q, -1);
+  CU_TRY(cudaMemsetAsync(h->best_val.p, 0, q * 8, st));
+  CU_TRY(cudaMemcpyAsync(h->best_idx.p, bi.data(), q * 8, cudaMemcpyHostToDevice, st));
+  CU_TRY(cudaStreamSynchronize(st));  // pr / bi are stack-owned
+  return 0;
+}
+
+static int download_best(b200bo_handle h, int q, double* best_val, int64_t* best_idx) {
+  cudaStream_t st = h->stream;
+  std::vector<long long> bi(q);
+  CU_TRY(cudaMemcpyAsync(best_val, h->best_val.p, q * 8, cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaMemcpyAsync(bi.data(), h->best_idx.p, q * 8, cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  for (int c = 0; c < q; ++c) best_idx[c] = bi[c];
+  return 0;
+}
+
+// Shared driver of predict / acq on the fp64 path.  acq_id < 0: predict only.
+static int run_candidates_fp64(b200bo_handle h, const double* Xc, int64_t M, int loc, int eval_mse, double* yhat_out,
+                               double* mse_out, int acq_id, int minimize, double plugin, const double* params, int q,
+                               double* vals, double* best_val, int64_t* best_idx) {
+  const bool do_acq = acq_id >= 0;
+  const bool dev = loc == B200BO_DEVICE;
+  int rc = ensure_predict_ws(h, q, do_acq && vals && !dev);
+  if (rc) return rc;
+  cudaStream_t st = h->stream;
+  const int D = h->D, Mc = h->Mc;
+  h->evs.reset();
+  PhaseTimer pt{h};
+  LaunchCount lc;
+  if (do_acq && (rc = upload_params_reset_best(h, params, q))) return rc;
   cudaEvent_t e0 = h->evs.get(), e1 = h->evs.get();
   CU_TRY(cudaEventRecord(e0, st));
   for (int64_t a = 0; a < M; a += Mc) {
     const int m = (int)std::min<int64_t>(Mc, M - a);
-    const int mpad = round_up(m, PC_BM);
     const double* xc = Xc + (size_t)a * D;
     if (!dev) {
       CU_TRY(cudaMemcpyAsync(h->Xc.p, xc, (size_t)m * D * 8, cudaMemcpyHostToDevice, st));
       xc = h->Xc.p;
     }
     double* yh = (dev && yhat_out) ? yhat_out + a : h->yhat.p;
-    pt.begin(0);
-    {
-      KstarArgs k;
-      k.Xc = xc; k.Xt = h->Xt.p; k.theta = h->theta.p; k.gamma = h->gamma.p;
-      k.Kst = eval_mse ? h->Kst.p : nullptr; k.yhat = yh;
-      k.M = m; k.N = h->N; k.D = D; k.ld = ld; k.corr = h->corr; k.beta = h->beta;
-      kstar_kernel<<<mpad / KS_ROWS, 256, ks_smem, st>>>(k);
-      CU_TRY(cudaGetLastError());
-      ++launches;
-    }
-    pt.end(0);
+    if ((rc = fp64_moments(h, xc, m, yh, eval_mse, &pt, &lc))) return rc;
     if (eval_mse) {
-      pt.begin(1);
-      ContractArgs c;
-      c.Kst = h->Kst.p; c.Linv = h->W.p; c.Ft = h->Ft.p; c.sumsq = h->sumsq.p; c.dotf = h->dotf.p; c.ld = ld;
-      contract_fp64_kernel<<<mpad / PC_BM, PredCore::NT, PredCore::SMEM_BYTES, st>>>(c);
-      CU_TRY(cudaGetLastError());
-      ++launches;
-      ++contract_launches;
-      pt.end(1);
       pt.begin(2);
-      AcqArgs g{};
-      g.yhat = yh; g.sumsq = h->sumsq.p; g.dotf = h->dotf.p; g.mse_in = nullptr;
-      g.mse_out = mse_out ? (dev ? mse_out + a : h->mse.p) : nullptr;
-      g.M = m; g.estimate_trend = h->estimate_trend; g.sigma2 = h->sigma2; g.G = h->G;
-      g.idx_base = a;
+      double* mo = mse_out ? (dev ? mse_out + a : h->mse.p) : nullptr;
       if (do_acq) {
-        g.vals = vals ? (dev ? vals : h->vals.p) : nullptr;
-        g.vals_ld = dev ? M : Mc;
-        g.vals_off = dev ? a : 0;
-        g.params = h->params.p; g.part_val = h->part_val.p; g.part_idx = h->part_idx.p;
-        g.acq = acq_id; g.minimize = minimize; g.q = q; g.plugin = plugin;
-        int nblk = std::min(h->num_sms, (m + 255) / 256);
-        acq_kernel<<<dim3(nblk, q), 256, 0, st>>>(g);
-        CU_TRY(cudaGetLastError());
-        argmax_merge_kernel<<<(q + 63) / 64, 64, 0, st>>>(h->part_val.p, h->part_idx.p, nblk, q, h->best_val.p, h->best_idx.p);
-        CU_TRY(cudaGetLastError());
-        launches += 2;
+        double* vp = vals ? (dev ? vals : h->vals.p) : nullptr;
+        if ((rc = acq_stage(h, yh, m, a, nullptr, acq_id, minimize, plugin, q, vp, dev ? M : Mc, dev ? a : 0, mo, &lc)))
+          return rc;
       } else {
+        AcqArgs g{};
+        g.yhat = yh; g.sumsq = h->sumsq.p; g.dotf = h->dotf.p; g.mse_out = mo;
+        g.M = m; g.estimate_trend = h->estimate_trend; g.sigma2 = h->sigma2; g.G = h->G;
         mse_kernel<<<std::min(h->num_sms, (m + 255) / 256), 256, 0, st>>>(g);
         CU_TRY(cudaGetLastError());
-        ++launches;
+        ++lc.all;
       }
       pt.end(2);
     }
@@ -648,22 +711,376 @@ static int run_candidates(b200bo_handle h, const double* Xc, int64_t M, int loc,
     }
   }
   CU_TRY(cudaEventRecord(e1, st));
-  if (do_acq) {
-    std::vector<long long> bi(q);
-    CU_TRY(cudaMemcpyAsync(best_val, h->best_val.p, q * 8, cudaMemcpyDeviceToHost, st));
-    CU_TRY(cudaMemcpyAsync(bi.data(), h->best_idx.p, q * 8, cudaMemcpyDeviceToHost, st));
-    CU_TRY(cudaStreamSynchronize(st));
-    for (int c = 0; c < q; ++c) best_idx[c] = bi[c];
-  }
+  if (do_acq && (rc = download_best(h, q, best_val, best_idx))) return rc;
   CU_TRY(cudaStreamSynchronize(st));
   float ms = 0;
   cudaEventElapsedTime(&ms, e0, e1);
   h->timings[0] = ms;
   for (int k = 0; k < 3; ++k) h->timings[1 + k] = pt.total(k);
-  h->timings[4] = contract_launches;
-  h->timings[5] = launches;
+  h->timings[4] = lc.contract;
+  h->timings[5] = lc.all;
   h->timings[6] = 0;
+  h->timings[7] = 0;
   return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// tensor-core path (B200BO_PREC_FAST)
+// ------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_linv_map(CUtensorMap* map, const __half* base, int ld) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CU_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres));
+    if (!f || qres != cudaDriverEntryPointSuccess) return set_err(B200BO_E_CUDA, "cuTensorMapEncodeTiled is not available");
+    fn = (EncodeTiledFn)f;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)ld};  // innermost first: k, then the row n of L^-1
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(__half)};
+  cuuint32_t box[2] = {(cuuint32_t)fk::KC, (cuuint32_t)fk::BN};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)base, dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_err(B200BO_E_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
+  return 0;
+}
+
+static bool fast_supported(const b200bo_ctx* h) { return h->corr != CUBIC && h->D <= 64; }
+
+static int ensure_fast_state(b200bo_handle h) {
+  if (h->fast_ready) return 0;
+  cudaStream_t st = h->stream;
+  const int D = h->D, ld = h->ld;
+  const size_t nn = (size_t)ld * ld;
+  h->DP = D <= 8 ? 8 : D <= 16 ? 16 : D <= 32 ? 32 : 64;
+  // per-feature coordinate scale folding theta (and log2 e / 2 nu) into the coordinates
+  std::vector<double> th(D), cs(D);
+  CU_TRY(cudaMemcpyAsync(th.data(), h->theta.p, D * 8, cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  const double LOG2E = 1.4426950408889634;
+  for (int d = 0; d < D; ++d) {
+    switch (h->corr) {
+      case RBF: cs[d] = sqrt(th[d] * LOG2E); break;
+      case MATERN12: cs[d] = sqrt(th[d]); break;
+      case MATERN32: cs[d] = sqrt(3.0 * th[d]); break;
+      case MATERN52: cs[d] = sqrt(5.0 * th[d]); break;
+      default: cs[d] = th[d] * LOG2E; break;  // ABSEXP
+    }
+  }
+  CU_TRY(h->cscale.reserve(D));
+  CU_TRY(cudaMemcpyAsync(h->cscale.p, cs.data(), D * 8, cudaMemcpyHostToDevice, st));
+  // f = L^-T Ft, so that Ft^T (L^-1 r) = r . f  (gpr.py:498 as a dot product against r)
+  CU_TRY(h->fvec.reserve(ld));
+  const int gchunks = (ld + 255) / 256;
+  CU_TRY(h->part.reserve((size_t)gchunks * ld));
+  tri_gemvT_partial_kernel<<<dim3((ld + 255) / 256, gchunks), 256, 0, st>>>(h->W.p, ld, ld, h->Ft.p, h->part.p, 256);
+  CU_TRY(cudaGetLastError());
+  colsum_partials_kernel<<<(ld + 255) / 256, 256, 0, st>>>(h->part.p, ld, gchunks, h->fvec.p);
+  CU_TRY(cudaGetLastError());
+  // power-of-two scale of L^-1 into the fp16 range, then the (hi, lo) split
+  const int nblk = h->num_sms * 4;
+  CU_TRY(h->errout.reserve(std::max(nblk, 8)));
+  fk::absmax_kernel<<<nblk, 256, 0, st>>>(h->W.p, nn, h->errout.p);
+  CU_TRY(cudaGetLastError());
+  std::vector<double> pm(nblk);
+  CU_TRY(cudaMemcpyAsync(pm.data(), h->errout.p, nblk * 8, cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  double mx = 0;
+  for (double v : pm) mx = std::max(mx, v);
+  if (!(mx > 0) || !std::isfinite(mx)) return set_err(B200BO_E_STATE, "L^-1 has no finite non-zero entry");
+  h->b_scale_log2 = 14 - ilogb(mx);
+  CU_TRY(h->Lh.reserve(nn));
+  CU_TRY(h->Ll.reserve(nn));
+  fk::linv_split_kernel<<<h->num_sms * 8, 256, 0, st>>>(h->W.p, nn, ldexp(1.0, h->b_scale_log2), h->Lh.p, h->Ll.p);
+  CU_TRY(cudaGetLastError());
+  CU_TRY(h->Xs.reserve((size_t)(h->DP + 2) * ld));
+  fk::xs_prep_kernel<<<(ld + 127) / 128, 128, 0, st>>>(h->Xt.p, h->cscale.p, h->gamma.p, h->fvec.p, D, h->DP, ld, h->Xs.p);
+  CU_TRY(cudaGetLastError());
+  int rc;
+  if ((rc = make_linv_map(&h->map_hi, h->Lh.p, ld))) return rc;
+  if ((rc = make_linv_map(&h->map_lo, h->Ll.p, ld))) return rc;
+  CU_TRY(h->err_flag.reserve(1));
+  CU_TRY(cudaMemsetAsync(h->err_flag.p, 0, sizeof(int), st));
+  if (!h->copy_stream) {
+    CU_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      CU_TRY(cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming));
+      CU_TRY(cudaEventCreateWithFlags(&h->ev_used[i], cudaEventDisableTiming));
+    }
+  }
+  CU_TRY(cudaStreamSynchronize(st));
+  h->fast_ready = true;
+  h->calibrated = false;
+  return 0;
+}
+
+// one launch of the fused tensor-core kernel over m device-resident candidates; outputs at out_off
+static int launch_fused(b200bo_handle h, const double* xc_dev, long long m, size_t out_off) {
+  fk::FusedArgs a;
+  a.Xc = xc_dev; a.Xs = h->Xs.p; a.cscale = h->cscale.p;
+  a.yhat = h->f_yhat.p + out_off; a.sumsq = h->f_sumsq.p + out_off; a.dotf = h->f_dotf.p + out_off;
+  a.dbg_w = h->want_dbg_w ? h->dbg_w.p : nullptr;
+  a.err = h->err_flag.p;
+  a.M = m; a.N = h->N; a.D = h->D; a.ld = h->ld; a.corr = h->corr; a.beta = h->beta;
+  a.out_scale = (float)ldexp(1.0, -(fk::A_SCALE_LOG2 + h->b_scale_log2));
+  const long long tiles = (m + fk::BM - 1) / fk::BM;
+  const int grid = (int)std::min<long long>(h->num_sms, tiles);
+  const int smem = fk::smem_total(h->DP);
+  const bool abs_ = h->corr == ABSEXP;
+#define FK_LAUNCH(DPV, ABSV)                                                                                     \
+  do {                                                                                                           \
+    auto kern = fk::predict_fused_tc_kernel<DPV, ABSV>;                                                          \
+    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fk::smem_total(DPV)));        \
+    kern<<<grid, fk::NT, smem, h->stream>>>(h->map_hi, h->map_lo, a);                                            \
+  } while (0)
+  switch (h->DP) {
+    case 8: if (abs_) FK_LAUNCH(8, true); else FK_LAUNCH(8, false); break;
+    case 16: if (abs_) FK_LAUNCH(16, true); else FK_LAUNCH(16, false); break;
+    case 32: if (abs_) FK_LAUNCH(32, true); else FK_LAUNCH(32, false); break;
+    default: if (abs_) FK_LAUNCH(64, true); else FK_LAUNCH(64, false); break;
+  }
+#undef FK_LAUNCH
+  CU_TRY(cudaGetLastError());
+  return 0;
+}
+
+static int check_fast_err(b200bo_handle h) {
+  int flag = 0;
+  CU_TRY(cudaMemcpyAsync(&flag, h->err_flag.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  if (flag) return set_err(B200BO_E_CUDA, "tensor-core pipeline wait timed out (code " + std::to_string(flag) + ")");
+  return 0;
+}
+
+// max |fast - exact| over n band (or leading) candidates; exact moments are in (h->yhat, h->sumsq, h->dotf)
+static int fast_errors(b200bo_handle h, const long long* list_dev, long long idx_base, int n, double* ey, double* es) {
+  fk::band_err_kernel<<<1, 256, 0, h->stream>>>(h->f_yhat.p, h->f_sumsq.p, h->f_dotf.p, h->yhat.p, h->sumsq.p,
+                                                 h->dotf.p, list_dev, idx_base, n, h->estimate_trend, h->G,
+                                                 h->sigma2, h->errout.p);
+  CU_TRY(cudaGetLastError());
+  double e[2];
+  CU_TRY(cudaMemcpyAsync(e, h->errout.p, 16, cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  *ey = e[0];
+  *es = e[1];
+  return 0;
+}
+
+static const int FAST_CHUNK_TILES = 8;        // candidate tiles per SM per fused launch when streaming from the host
+static const int BAND_CAP = 1 << 18;          // most candidates the exact re-score accepts before falling back
+static const int BAND_CHUNK = 1 << 20;        // candidates per band_bounds launch (bounds the q x chunk fp32 scratch)
+
+static int run_candidates_fast(b200bo_handle h, const double* Xc, int64_t M, int loc, int eval_mse, double* yhat_out,
+                               double* mse_out, int acq_id, int minimize, double plugin, const double* params, int q,
+                               double* best_val, int64_t* best_idx, bool* fell_back) {
+  *fell_back = false;
+  const bool do_acq = acq_id >= 0;
+  const bool dev = loc == B200BO_DEVICE;
+  int rc;
+  if ((rc = ensure_fast_state(h))) return rc;
+  if ((rc = ensure_predict_ws(h, q, false))) return rc;
+  cudaStream_t st = h->stream;
+  const int D = h->D, Mc = h->Mc;
+  const size_t Mpad = (size_t)round_up((int)std::min<int64_t>(M, INT32_MAX - 256), fk::BM);
+  CHECK_ARG(M < INT32_MAX - 256, "M too large for one call");
+  CU_TRY(h->f_yhat.reserve(Mpad + fk::BM));
+  CU_TRY(h->f_sumsq.reserve(Mpad + fk::BM));
+  CU_TRY(h->f_dotf.reserve(Mpad + fk::BM));
+  if (h->want_dbg_w) CU_TRY(h->dbg_w.reserve(Mpad * (size_t)h->ld));
+  h->evs.reset();
+  PhaseTimer pt{h};
+  LaunchCount lc;
+  int fused_launches = 0;
+  if (do_acq && (rc = upload_params_reset_best(h, params, q))) return rc;
+  cudaEvent_t e0 = h->evs.get(), e1 = h->evs.get();
+  CU_TRY(cudaEventRecord(e0, st));
+
+  // ---- phase I: the fused tensor-core pass over all candidates ---------------------------------------
+  pt.begin(1);
+  if (dev) {
+    if ((rc = launch_fused(h, Xc, M, 0))) return rc;
+    ++fused_launches;
+  } else {
+    // stream the host candidates through two staging buffers; copies run on their own stream
+    const int64_t FMc = (int64_t)h->num_sms * fk::BM * FAST_CHUNK_TILES;
+    for (int i = 0; i < 2; ++i) CU_TRY(h->stage[i].reserve((size_t)std::min<int64_t>(FMc, M) * D));
+    int64_t i = 0;
+    for (int64_t a = 0; a < M; a += FMc, ++i) {
+      const int64_t m = std::min<int64_t>(FMc, M - a);
+      const int b = (int)(i & 1);
+      if (i >= 2) CU_TRY(cudaStreamWaitEvent(h->copy_stream, h->ev_used[b], 0));
+      else if (i == 0) {
+        // order the first copy after whatever the compute stream did before (set_train / factor)
+        CU_TRY(cudaEventRecord(h->ev_used[0], st));
+        CU_TRY(cudaStreamWaitEvent(h->copy_stream, h->ev_used[0], 0));
+      }
+      CU_TRY(cudaMemcpyAsync(h->stage[b].p, Xc + (size_t)a * D, (size_t)m * D * 8, cudaMemcpyHostToDevice, h->copy_stream));
+      CU_TRY(cudaEventRecord(h->ev_copied[b], h->copy_stream));
+      CU_TRY(cudaStreamWaitEvent(st, h->ev_copied[b], 0));
+      if ((rc = launch_fused(h, h->stage[b].p, m, (size_t)a))) return rc;
+      CU_TRY(cudaEventRecord(h->ev_used[b], st));
+      ++fused_launches;
+    }
+  }
+  pt.end(1);
+  lc.all += fused_launches;
+
+  if (!do_acq) {
+    // predict(): moments of the fast pass, MSE elementwise (approximate; see include/b200bo.h)
+    AcqArgs g{};
+    g.yhat = h->f_yhat.p; g.sumsq = h->f_sumsq.p; g.dotf = h->f_dotf.p;
+    g.M = (int)M; g.estimate_trend = h->estimate_trend; g.sigma2 = h->sigma2; g.G = h->G;
+    double* mo = nullptr;
+    if (eval_mse) {
+      if (dev) mo = mse_out;
+      else { CU_TRY(h->f_sumsq.reserve(Mpad + fk::BM)); mo = h->f_sumsq.p; }  // overwrite in place, then copy out
+      g.mse_out = mo;
+      mse_kernel<<<std::min(h->num_sms * 4, (int)((M + 255) / 256)), 256, 0, st>>>(g);
+      CU_TRY(cudaGetLastError());
+      ++lc.all;
+    }
+    const cudaMemcpyKind kind = dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    if (yhat_out) CU_TRY(cudaMemcpyAsync(yhat_out, h->f_yhat.p, (size_t)M * 8, kind, st));
+    if (eval_mse && !dev) CU_TRY(cudaMemcpyAsync(mse_out, mo, (size_t)M * 8, kind, st));
+    CU_TRY(cudaEventRecord(e1, st));
+    if ((rc = check_fast_err(h))) return rc;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    h->timings[0] = ms; h->timings[1] = 0; h->timings[2] = pt.total(1); h->timings[3] = 0;
+    h->timings[4] = fused_launches; h->timings[5] = lc.all; h->timings[6] = 0; h->timings[7] = 0;
+    return 0;
+  }
+  if ((rc = check_fast_err(h))) return rc;
+
+  // ---- calibration of the error half-widths (once per factor()): fast vs fp64 on the leading candidates -
+  pt.begin(2);
+  auto host_rows_to = [&](double* dst_dev, const long long* idx, int n) -> int {  // gather host rows, upload
+    std::vector<double> tmp((size_t)n * D);
+    for (int b = 0; b < n; ++b) memcpy(&tmp[(size_t)b * D], Xc + (size_t)idx[b] * D, (size_t)D * 8);
+    CU_TRY(cudaMemcpyAsync(dst_dev, tmp.data(), tmp.size() * 8, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    return 0;
+  };
+  if (!h->calibrated) {
+    const int n = (int)std::min<int64_t>(M, std::min(Mc, 2048));
+    const double* xc = Xc;
+    if (!dev) {
+      CU_TRY(cudaMemcpyAsync(h->Xc.p, Xc, (size_t)n * D * 8, cudaMemcpyHostToDevice, st));
+      xc = h->Xc.p;
+    }
+    if ((rc = fp64_moments(h, xc, n, h->yhat.p, 1, nullptr, &lc))) return rc;
+    double ey, es;
+    if ((rc = fast_errors(h, nullptr, 0, n, &ey, &es))) return rc;
+    h->dy_cal = 8.0 * ey + 1e-13;
+    h->ds_cal = 8.0 * es + 1e-13 * h->sigma2;
+    h->calibrated = true;
+  }
+
+  // ---- phase II / III: band selection, exact re-score; widen and repeat if the band shows larger errors --
+  CU_TRY(h->thr.reserve(q));
+  CU_TRY(h->band_list.reserve(BAND_CAP));
+  CU_TRY(h->band_count.reserve(1));
+  const int bchunk = (int)std::min<int64_t>(BAND_CHUNK, M);
+  CU_TRY(h->band_hi.reserve((size_t)q * bchunk));
+  const int nblk_b = std::min(h->num_sms * 2, (bchunk + 255) / 256);
+  CU_TRY(h->thr_part.reserve((size_t)q * nblk_b));
+  CU_TRY(h->Xband.reserve((size_t)Mc * D));
+  int rescored = 0, passes = 0;
+  double dy = h->dy_cal, ds = h->ds_cal;
+  std::vector<long long> list;
+  for (;;) {
+    ++passes;
+    std::vector<double> ninf(q, -INFINITY);
+    CU_TRY(cudaMemcpyAsync(h->thr.p, ninf.data(), q * 8, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemsetAsync(h->band_count.p, 0, sizeof(int), st));
+    CU_TRY(cudaStreamSynchronize(st));
+    for (int64_t a = 0; a < M; a += bchunk) {
+      const int m = (int)std::min<int64_t>(bchunk, M - a);
+      fk::BandArgs b;
+      b.yhat = h->f_yhat.p + a; b.sumsq = h->f_sumsq.p + a; b.dotf = h->f_dotf.p + a; b.params = h->params.p;
+      b.hi = h->band_hi.p; b.thr_part = h->thr_part.p;
+      b.M = m; b.acq = acq_id; b.minimize = minimize; b.estimate_trend = h->estimate_trend; b.q = q;
+      b.sigma2 = h->sigma2; b.plugin = plugin; b.G = h->G; b.dy = dy; b.ds = ds;
+      const int nb = std::min(h->num_sms * 2, (m + 255) / 256);
+      fk::band_bounds_kernel<<<dim3(nb, q), 256, 0, st>>>(b);
+      CU_TRY(cudaGetLastError());
+      fk::band_thr_merge_kernel<<<(q + 63) / 64, 64, 0, st>>>(h->thr_part.p, nb, q, h->thr.p);
+      CU_TRY(cudaGetLastError());
+      fk::band_flag_kernel<<<nb, 256, 0, st>>>(h->band_hi.p, h->thr.p, m, q, a, h->band_list.p, BAND_CAP, h->band_count.p);
+      CU_TRY(cudaGetLastError());
+      lc.all += 3;
+    }
+    int count = 0;
+    CU_TRY(cudaMemcpyAsync(&count, h->band_count.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    if (count > BAND_CAP || passes > 4) {  // degenerate (flat criterion) or unstable error estimate
+      *fell_back = true;
+      return 0;
+    }
+    list.resize(count);
+    CU_TRY(cudaMemcpyAsync(list.data(), h->band_list.p, (size_t)count * 8, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    // exact fp64 moments + criteria of the band, Mc rows at a time; arg-max merged with the global indices
+    if ((rc = upload_params_reset_best(h, params, q))) return rc;
+    double ey_max = 0, es_max = 0;
+    for (int o = 0; o < count; o += Mc) {
+      const int m = std::min(Mc, count - o);
+      if (dev) {
+        fk::band_gather_kernel<<<(m * D + 255) / 256, 256, 0, st>>>(Xc, h->band_list.p + o, m, 0, D, h->Xband.p);
+        CU_TRY(cudaGetLastError());
+        ++lc.all;
+      } else if ((rc = host_rows_to(h->Xband.p, list.data() + o, m))) {
+        return rc;
+      }
+      if ((rc = fp64_moments(h, h->Xband.p, m, h->yhat.p, 1, nullptr, &lc))) return rc;
+      if ((rc = acq_stage(h, h->yhat.p, m, 0, h->band_list.p + o, acq_id, minimize, plugin, q, nullptr, 0, 0, nullptr, &lc)))
+        return rc;
+      double ey, es;
+      if ((rc = fast_errors(h, h->band_list.p + o, 0, m, &ey, &es))) return rc;
+      ey_max = std::max(ey_max, ey);
+      es_max = std::max(es_max, es);
+    }
+    rescored += count;
+    if (ey_max <= 0.5 * dy && es_max <= 0.5 * ds) break;  // the band was wide enough for the errors it shows
+    dy = std::max(dy, 4.0 * ey_max);
+    ds = std::max(ds, 4.0 * es_max);
+    h->dy_cal = std::max(h->dy_cal, dy);
+    h->ds_cal = std::max(h->ds_cal, ds);
+  }
+  pt.end(2);
+  CU_TRY(cudaEventRecord(e1, st));
+  if ((rc = download_best(h, q, best_val, best_idx))) return rc;
+  CU_TRY(cudaStreamSynchronize(st));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  h->timings[0] = ms; h->timings[1] = 0; h->timings[2] = pt.total(1); h->timings[3] = pt.total(2);
+  h->timings[4] = fused_launches; h->timings[5] = lc.all; h->timings[6] = rescored; h->timings[7] = passes;
+  return 0;
+}
+
+static int run_candidates(b200bo_handle h, const double* Xc, int64_t M, int loc, int eval_mse, double* yhat_out,
+                          double* mse_out, int acq_id, int minimize, double plugin, const double* params, int q,
+                          double* vals, double* best_val, int64_t* best_idx) {
+  CHECK_ARG(h, "handle is NULL");
+  if (!h->factored) return set_err(B200BO_E_STATE, "predict before a successful factor()");
+  CHECK_ARG(M >= 0, "M < 0");
+  CHECK_ARG(loc == B200BO_HOST || loc == B200BO_DEVICE, "bad loc");
+  CU_TRY(cudaSetDevice(h->device));
+  // the tensor-core pass needs the variance (its product is rt) and cannot return all q x M values exactly
+  if (h->prec == B200BO_PREC_FAST && fast_supported(h) && eval_mse && !vals && M > 0) {
+    bool fell_back = false;
+    int rc = run_candidates_fast(h, Xc, M, loc, eval_mse, yhat_out, mse_out, acq_id, minimize, plugin, params, q,
+                                 best_val, best_idx, &fell_back);
+    if (rc || !fell_back) return rc;
+  }
+  return run_candidates_fp64(h, Xc, M, loc, eval_mse, yhat_out, mse_out, acq_id, minimize, plugin, params, q, vals,
+                             best_val, best_idx);
 }
 
 int b200bo_predict(b200bo_handle h, const double* Xc, int64_t M, int loc, int eval_mse, double* yhat, double* mse) {
@@ -733,6 +1150,37 @@ int b200bo_acq_from_moments(b200bo_handle h, const double* yhat, const double* m
   CU_TRY(cudaMemcpyAsync(bi.data(), h->best_idx.p, q * 8, cudaMemcpyDeviceToHost, st));
   CU_TRY(cudaStreamSynchronize(st));
   for (int c = 0; c < q; ++c) best_idx[c] = bi[c];
+  return 0;
+}
+
+int b200bo_debug_fast_rt(b200bo_handle h, const double* Xc, int64_t M, float* out_rt, double* yhat, double* sumsq,
+                         double* dotf) {
+  CHECK_ARG(h && Xc && out_rt, "NULL argument");
+  if (!h->factored) return set_err(B200BO_E_STATE, "debug_fast_rt before a successful factor()");
+  CHECK_ARG(M >= 1 && M <= 65536, "M out of range for the debug hook");
+  CHECK_ARG(fast_supported(h), "the tensor-core path does not cover this kernel / feature count");
+  CU_TRY(cudaSetDevice(h->device));
+  int rc;
+  if ((rc = ensure_fast_state(h))) return rc;
+  const size_t Mpad = (size_t)round_up((int)M, fk::BM);
+  const int D = h->D, ld = h->ld, N = h->N;
+  CU_TRY(h->f_yhat.reserve(Mpad + fk::BM));
+  CU_TRY(h->f_sumsq.reserve(Mpad + fk::BM));
+  CU_TRY(h->f_dotf.reserve(Mpad + fk::BM));
+  CU_TRY(h->dbg_w.reserve(Mpad * (size_t)ld));
+  CU_TRY(h->stage[0].reserve((size_t)M * D));
+  CU_TRY(cudaMemcpyAsync(h->stage[0].p, Xc, (size_t)M * D * 8, cudaMemcpyHostToDevice, h->stream));
+  h->want_dbg_w = true;
+  rc = launch_fused(h, h->stage[0].p, M, 0);
+  h->want_dbg_w = false;
+  if (rc) return rc;
+  if ((rc = check_fast_err(h))) return rc;
+  CU_TRY(cudaMemcpy2DAsync(out_rt, (size_t)N * 4, h->dbg_w.p, (size_t)ld * 4, (size_t)N * 4, (size_t)M,
+                           cudaMemcpyDeviceToHost, h->stream));
+  if (yhat) CU_TRY(cudaMemcpyAsync(yhat, h->f_yhat.p, (size_t)M * 8, cudaMemcpyDeviceToHost, h->stream));
+  if (sumsq) CU_TRY(cudaMemcpyAsync(sumsq, h->f_sumsq.p, (size_t)M * 8, cudaMemcpyDeviceToHost, h->stream));
+  if (dotf) CU_TRY(cudaMemcpyAsync(dotf, h->f_dotf.p, (size_t)M * 8, cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(cudaStreamSynchronize(h->stream));
   return 0;
 }
 

@@ -174,6 +174,7 @@ struct AcqArgs {
   double* part_val;      // (q, gridDim.x)
   long long* part_idx;   // (q, gridDim.x)
   long long idx_base;    // global index of candidate 0 of this chunk
+  const long long* idx_map;  // NULL, or global index of candidate i (re-scored band of the fast path)
   int M, acq, minimize, estimate_trend, q;
   double sigma2, plugin, G;  // G: the 1x1 triangular factor of the thin QR of Ft (|G| = ||Ft||)
 };
@@ -201,7 +202,7 @@ __global__ void __launch_bounds__(256) acq_kernel(AcqArgs p) {
     if (c == 0 && p.mse_out) p.mse_out[i] = mse;
     double v = acq_value(p.acq, p.yhat[i], mse, p.sigma2, p.plugin, par, p.minimize);
     if (p.vals) p.vals[(size_t)c * p.vals_ld + p.vals_off + i] = v;
-    long long gi = p.idx_base + i;
+    long long gi = p.idx_map ? p.idx_map[i] : p.idx_base + i;
     if (bi < 0 || arg_better(v, gi, bv, bi)) {
       bv = v;
       bi = gi;

@@ -61,8 +61,10 @@ class GaussianProcess:
 
     def __init__(self, mean=None, corr="squared_exponential", theta0=None, thetaL=None, thetaU=None, sigma2=None,
                  nugget=1e-6, noise_estim=False, optimizer="BFGS", likelihood="concentrated", random_start=1,
-                 wait_iter=5, eval_budget=None, random_state=None, verbose=False, device: int = 0):
-        # gpr.py:229-277
+                 wait_iter=5, eval_budget=None, random_state=None, verbose=False, device: int = 0,
+                 precision: str = "fp64"):
+        # gpr.py:229-277; ``device`` and ``precision`` are the only additions.  precision="fast": predict /
+        # acquisition arg-max run the tcgen05 tensor-core pass (arg-max still exact via the fp64 re-score)
         self.mean = mean
         self.corr = corr
         self.sigma2 = sigma2
@@ -99,6 +101,9 @@ class GaussianProcess:
         else:
             raise ValueError("only BasisExpansionTrend means have a device implementation")
         self.device = int(device)
+        if precision not in ("fp64", "fast"):
+            raise ValueError("precision should be 'fp64' or 'fast', %s was given." % precision)
+        self.precision = precision
         self._engine: Optional[Engine] = None
         self._cache = {}
 
@@ -107,6 +112,7 @@ class GaussianProcess:
     def engine(self) -> Engine:
         if self._engine is None:
             self._engine = Engine(self.device)  # raises without libb200bo.so / a B200
+            self._engine.set_precision(_lib.PREC_FAST if getattr(self, "precision", "fp64") == "fast" else _lib.PREC_FP64)
             if getattr(self, "X", None) is not None:
                 self._engine.set_train(self.X, self.y[:, 0])
                 if self.is_fitted:

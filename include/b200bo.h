@@ -64,7 +64,9 @@ typedef struct b200bo_ctx* b200bo_handle;
 
 /* precision of the M-candidate predict path */
 #define B200BO_PREC_FP64 0 /* fp64 DMMA, parity path (default)                                          */
-#define B200BO_PREC_FAST 1 /* split-bf16 tcgen05 tensor-core pass + fp64 re-score of the arg-max band   */
+#define B200BO_PREC_FAST 1 /* split-fp16 tcgen05 tensor-core pass (~1e-6) + fp64 re-score of the arg-max band:
+                              b200bo_acq returns the exact fp64 best_val / best_idx; b200bo_predict returns the
+                              approximate moments.  Calls that ask for all q x M values run on the fp64 path. */
 
 /* state ids for b200bo_get_state */
 #define B200BO_STATE_L 0     /* Cholesky factor "C"   (N,N) lower, zeros above   gpr.py:408, :795 */
@@ -136,11 +138,18 @@ int b200bo_acq_from_moments(b200bo_handle h, const double* yhat, const double* m
                             int acq_id, int minimize, double plugin, const double* params, int q,
                             double* vals, double* best_val, int64_t* best_idx);
 
+/* test hook of the tensor-core path: rt = L^-1 r^T exactly as the tcgen05 pipeline produced it, (M,N) float32,
+ * plus the three per-candidate outputs of the fused kernel (each may be NULL).  Host pointers, M <= 65536.
+ * What it checks against: solve_triangular(C, r.T) of gpr.py:494. */
+int b200bo_debug_fast_rt(b200bo_handle h, const double* Xc, int64_t M, float* out_rt, double* yhat, double* sumsq,
+                         double* dotf);
+
 /* -- instrumentation ------------------------------------------------------------------------------------
  * CUDA-event timings (ms) of the last predict/acq call, recorded on the handle's stream:
  *   [0] whole call on device  [1] k* build kernels  [2] L^-1 k* contraction kernels (the dominant kernel)
  *   [3] acquisition + arg-max kernels  [4] number of contraction launches  [5] number of all launches
- *   [6] fp64 re-scored candidates (FAST only) */
+ *   [6] fp64 re-scored candidates (FAST only)  [7] band passes (FAST only)
+ * FAST: [1] = 0 (the k* build is fused), [2] = fused tensor-core kernel, [3] = band selection + exact re-score */
 #define B200BO_N_TIMINGS 8
 int b200bo_get_timings(b200bo_handle h, double* out, int n);
 /* timings (ms) of the last factor(): [0] total [1] assembly [2] cholesky [3] trtri [4] solves  [5] launches */

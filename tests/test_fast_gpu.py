@@ -1,0 +1,127 @@
+"""GPU parity of the tensor-core path (B200BO_PREC_FAST): tcgen05 split-fp16 pass + exact fp64 re-score.
+
+  * rt = L^-1 r^T as the tcgen05 pipeline produced it, against the oracle's solve_triangular (gpr.py:494):
+    |d rt| <= 2e-5 max|rt| + 1e-6 ||L^-1||_inf -- catches any operand-layout / pipeline mistake element by element;
+  * fast moments: |d yhat| <= 1e-3, |d MSE| <= 1e-4 sigma2 (the documented tolerance of the fast predict);
+  * acquisition arg-max: index bit-exact and value to fp64 tolerance (1e-7 rel), because the band is re-scored
+    on the fp64 path -- the same bar as the fp64 path itself.
+"""
+import numpy as np
+import pytest
+import scipy.linalg
+
+import bayesian_optimization_b200 as b2
+from bayesian_optimization_b200 import _lib, workloads
+from oracle import gp_oracle as go
+
+pytestmark = pytest.mark.gpu
+
+CASES = [  # (N, D, corr name, oracle corr id)
+    (512, 8, "squared_exponential", go.CORR_RBF),
+    (640, 5, "matern52", go.CORR_MATERN52),
+    (1100, 16, "matern32", go.CORR_MATERN32),
+    (300, 3, "matern12", go.CORR_MATERN12),
+    (700, 24, "absolute_exponential", go.CORR_ABSEXP),
+    (2048, 40, "squared_exponential", go.CORR_RBF),
+]
+
+
+def make(N, D, corr, corr_id, nugget=1e-6):
+    X, y, theta = workloads.canonical_problem(N, D)
+    gp = b2.GaussianProcess(mean=b2.constant_trend(D), corr=corr, thetaL=[1e-5] * D, thetaU=[1e2] * D, nugget=nugget)
+    gp.fit_fixed(X, y, theta, 1.0)
+    ora = go.fit_fixed(X, y, corr_id, theta, go.MODE_NOISY, sigma2=1.0, noise_var=nugget)
+    return gp, ora
+
+
+@pytest.mark.parametrize("N,D,corr,corr_id", CASES)
+def test_rt_and_moments(N, D, corr, corr_id):
+    gp, ora = make(N, D, corr, corr_id)
+    M = 300  # ragged: not a multiple of the 128-row tile
+    Xc = workloads.canonical_candidates(M, D)
+    rt, yh, ss, df = gp.engine.debug_fast_rt(Xc)
+    r = go.corr_values(ora.corr, ora.theta, go.cross_abs_diff(Xc, ora.X)).reshape(M, N)
+    rt_ref = scipy.linalg.solve_triangular(ora.L, r.T, lower=True).T     # (M, N)
+    scale = np.abs(rt_ref).max()
+    err = np.abs(rt - rt_ref).max()
+    # r is built in fp32 (relative error ~5e-7 per element); L^-1 amplifies it by at most its inf-norm
+    amp = np.abs(np.linalg.inv(ora.L)).sum(axis=1).max()
+    assert err <= 2e-5 * scale + 1e-6 * amp, (err, scale, amp)
+    yo, mo = go.predict_chunked(ora, Xc, 512)
+    yo, mo = yo.ravel(), mo.ravel()
+    assert np.abs(yh - yo).max() <= 1e-3
+    np.testing.assert_allclose(ss, (rt_ref ** 2).sum(axis=1), rtol=0, atol=1e-4)
+    np.testing.assert_allclose(df, rt_ref @ ora.Ft.ravel(), rtol=0, atol=1e-4 * max(1.0, np.abs(ora.Ft).max()))
+
+
+@pytest.mark.parametrize("N,D,corr,corr_id", CASES[:3])
+def test_fast_predict_tolerance(N, D, corr, corr_id):
+    gp, ora = make(N, D, corr, corr_id)
+    Xc = workloads.canonical_candidates(5000, D)
+    gp.engine.set_precision(_lib.PREC_FAST)
+    yh, ms = gp.engine.predict(Xc, True)
+    yo, mo = go.predict_chunked(ora, Xc, 512)
+    yo, mo = yo.ravel(), mo.ravel()
+    assert np.abs(yh - yo).max() <= 1e-3
+    assert np.abs(ms - mo).max() <= 1e-4 * ora.sigma2
+    assert (ms >= 0).all()
+
+
+@pytest.mark.parametrize("acq,params", [
+    (_lib.ACQ_EI, [0.0]),
+    (_lib.ACQ_MGFI, [0.1, 0.5, 1.0, 2.0, 5.0, 22.36, 40.0]),
+    (_lib.ACQ_UCB, [0.1, 0.5, 2.0]),
+    (_lib.ACQ_PI, [1e-10, 0.05]),
+])
+@pytest.mark.parametrize("N,D,corr,corr_id", CASES[:3])
+def test_fast_argmax_is_exact(N, D, corr, corr_id, acq, params):
+    gp, ora = make(N, D, corr, corr_id)
+    M = 60000
+    Xc = workloads.canonical_candidates(M, D)
+    yo, mo = go.predict_chunked(ora, Xc, 1024)
+    yo, mo = yo.ravel(), mo.ravel()
+    pl = go.plugin_value(ora.y, True)
+    eng = gp.engine
+    eng.set_precision(_lib.PREC_FAST)
+    bv, bi, _ = eng.acq(Xc, acq, True, pl, params)
+    t = eng.timings()
+    assert 1 <= t[6] < M, t            # something was re-scored, but not everything
+    for k, par in enumerate(params):
+        vo = go.acquisition(acq, yo, mo, ora.sigma2, pl, par, True)
+        assert int(bi[k]) == int(np.argmax(vo)), (k, par, bi[k], int(np.argmax(vo)), t)
+        assert bv[k] == pytest.approx(vo.max(), rel=1e-7, abs=1e-300)
+    # the fp64 path gives the same answer bit for bit (the re-score IS the fp64 path)
+    eng.set_precision(_lib.PREC_FP64)
+    bv2, bi2, _ = eng.acq(Xc, acq, True, pl, params)
+    np.testing.assert_array_equal(bi, bi2)
+    np.testing.assert_array_equal(bv, bv2)
+
+
+def test_fast_device_resident_and_maximize():
+    import torch
+
+    N, D = 512, 8
+    gp, ora = make(N, D, "squared_exponential", go.CORR_RBF)
+    M = 40000
+    Xc = workloads.canonical_candidates(M, D)
+    eng = gp.engine
+    pl = go.plugin_value(ora.y, False)
+    eng.set_precision(_lib.PREC_FP64)
+    ref = eng.acq(Xc, _lib.ACQ_EI, False, pl, [0.0])
+    eng.set_precision(_lib.PREC_FAST)
+    xd = torch.from_numpy(Xc).cuda()
+    got = eng.acq(xd, _lib.ACQ_EI, False, pl, [0.0])
+    assert int(got[1][0]) == int(ref[1][0]) and got[0][0] == ref[0][0]
+
+
+def test_fast_flat_criterion_falls_back():
+    """all EI values are 0 when the plug-in is far below every prediction... the band is everything -> fp64 path"""
+    N, D = 256, 4
+    gp, ora = make(N, D, "squared_exponential", go.CORR_RBF)
+    Xc = workloads.canonical_candidates(3000, D)
+    eng = gp.engine
+    eng.set_precision(_lib.PREC_FAST)
+    bv, bi, _ = eng.acq(Xc, _lib.ACQ_EI, True, -1e6, [0.0])
+    eng.set_precision(_lib.PREC_FP64)
+    bv2, bi2, _ = eng.acq(Xc, _lib.ACQ_EI, True, -1e6, [0.0])
+    assert int(bi[0]) == int(bi2[0]) and bv[0] == bv2[0]
