@@ -44,6 +44,7 @@ SIGNATURES = {
     "b200bo_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "b200bo_set_precision": (C.c_int, [C.c_void_p, C.c_int]),
     "b200bo_set_keep_R": (C.c_int, [C.c_void_p, C.c_int]),
+    "b200bo_set_fast_kernel": (C.c_int, [C.c_void_p, C.c_int]),
     "b200bo_set_train": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "b200bo_factor": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double,
                                 C.c_int, C.c_void_p, _dp, _dp, _dp, _ip]),
@@ -132,6 +133,9 @@ class Engine:
 
     def set_precision(self, prec: int):
         _check(self._lib.b200bo_set_precision(self._h, int(prec)))
+
+    def set_fast_kernel(self, generation: int):
+        _check(self._lib.b200bo_set_fast_kernel(self._h, int(generation)))
 
     def set_keep_R(self, keep: bool):
         _check(self._lib.b200bo_set_keep_R(self._h, int(bool(keep))))

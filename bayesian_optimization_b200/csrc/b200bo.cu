@@ -15,6 +15,7 @@
 #include "../../include/b200bo.h"
 #include "dgemm.cuh"
 #include "fast_kernels.cuh"
+#include "fast2_kernels.cuh"
 #include "fit_kernels.cuh"
 #include "predict_kernels.cuh"
 
@@ -118,6 +119,15 @@ struct b200bo_ctx {
   DevBuf<long long> band_list;
   DevBuf<int> band_count, err_flag;
   CUtensorMap map_hi, map_lo;
+  // second-generation kernel (Gram product on the tensor cores): its own operand copies
+  bool use_v2 = false;
+  DevBuf<__half> Xh2, Xl2;
+  DevBuf<float> aux2;
+  DevBuf<float2> exch2;
+  DevBuf<double> cmean;
+  CUtensorMap map2_hi, map2_lo, map2_xh, map2_xl;
+  std::vector<double> xmean;  // per-feature mean of the training set (host copy from set_train)
+  int fast_kernel_pref = 2;   // 2: newest kernel that covers the configuration; 1: force the first-generation kernel
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_used[2] = {nullptr, nullptr};
   bool want_dbg_w = false;
@@ -225,6 +235,7 @@ int b200bo_destroy(b200bo_handle h) {
   h->Xc.release(); h->Kst.release(); h->yhat.release(); h->sumsq.release(); h->dotf.release();
   h->mse.release(); h->params.release(); h->part_val.release(); h->best_val.release(); h->vals.release();
   h->part_idx.release(); h->best_idx.release();
+  h->Xh2.release(); h->Xl2.release(); h->aux2.release(); h->exch2.release(); h->cmean.release();
   h->Lh.release(); h->Ll.release(); h->Xs.release(); h->band_hi.release(); h->dbg_w.release();
   h->cscale.release(); h->fvec.release(); h->f_yhat.release(); h->f_sumsq.release(); h->f_dotf.release();
   h->stage[0].release(); h->stage[1].release(); h->thr.release(); h->thr_part.release(); h->Xband.release();
@@ -257,6 +268,15 @@ int b200bo_set_precision(b200bo_handle h, int prec) {
   return 0;
 }
 
+int b200bo_set_fast_kernel(b200bo_handle h, int generation) {
+  CHECK_ARG(h, "handle is NULL");
+  CHECK_ARG(generation == 1 || generation == 2, "generation is 1 or 2");
+  h->fast_kernel_pref = generation;
+  h->fast_ready = false;
+  h->calibrated = false;
+  return 0;
+}
+
 int b200bo_set_keep_R(b200bo_handle h, int keep) {
   CHECK_ARG(h, "handle is NULL");
   h->keepR = keep != 0;
@@ -274,6 +294,10 @@ int b200bo_set_train(b200bo_handle h, const double* X, const double* y, int N, i
   h->factored = false;
   const int ld = h->ld;
   std::vector<double> xt((size_t)D * ld, 0.0), yy(ld, 0.0), ff(ld, 0.0);
+  h->xmean.assign(D, 0.0);
+  for (int i = 0; i < N; ++i)
+    for (int d = 0; d < D; ++d) h->xmean[d] += X[(size_t)i * D + d];
+  for (int d = 0; d < D; ++d) h->xmean[d] /= N;
   for (int i = 0; i < N; ++i) {
     for (int d = 0; d < D; ++d) xt[(size_t)d * ld + i] = X[(size_t)i * D + d];
     yy[i] = y[i];
@@ -731,7 +755,12 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+static int make_f16_map(CUtensorMap* map, const __half* base, int inner, int rows, int box_inner, int box_rows);
 static int make_linv_map(CUtensorMap* map, const __half* base, int ld) {
+  return make_f16_map(map, base, ld, ld, fk::KC, fk::BN);
+}
+// 2-D fp16 row-major tensor (rows x inner), 128-byte-swizzled boxes of box_rows x box_inner
+static int make_f16_map(CUtensorMap* map, const __half* base, int inner, int rows, int box_inner, int box_rows) {
   static EncodeTiledFn fn = nullptr;
   if (!fn) {
     void* f = nullptr;
@@ -740,9 +769,9 @@ static int make_linv_map(CUtensorMap* map, const __half* base, int ld) {
     if (!f || qres != cudaDriverEntryPointSuccess) return set_err(B200BO_E_CUDA, "cuTensorMapEncodeTiled is not available");
     fn = (EncodeTiledFn)f;
   }
-  cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)ld};  // innermost first: k, then the row n of L^-1
-  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(__half)};
-  cuuint32_t box[2] = {(cuuint32_t)fk::KC, (cuuint32_t)fk::BN};
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)rows};  // innermost first (for L^-1: k, then the row n)
+  cuuint64_t strides[1] = {(cuuint64_t)inner * sizeof(__half)};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)base, dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -805,6 +834,22 @@ static int ensure_fast_state(b200bo_handle h) {
   int rc;
   if ((rc = make_linv_map(&h->map_hi, h->Lh.p, ld))) return rc;
   if ((rc = make_linv_map(&h->map_lo, h->Ll.p, ld))) return rc;
+  h->use_v2 = h->fast_kernel_pref >= 2 && h->corr != ABSEXP;
+  if (h->use_v2) {
+    CU_TRY(h->cmean.reserve(D));
+    CU_TRY(cudaMemcpyAsync(h->cmean.p, h->xmean.data(), D * 8, cudaMemcpyHostToDevice, st));
+    CU_TRY(h->Xh2.reserve((size_t)ld * 64));
+    CU_TRY(h->Xl2.reserve((size_t)ld * 64));
+    CU_TRY(h->aux2.reserve((size_t)(ld / fk::KC) * 3 * fk::KC));
+    CU_TRY(h->exch2.reserve((size_t)h->num_sms * 3 * fk::BM));
+    fk2::xs2_prep_kernel<<<(ld + 127) / 128, 128, 0, st>>>(h->Xt.p, h->cscale.p, h->cmean.p, h->gamma.p, h->fvec.p,
+                                                           h->N, D, ld, h->Xh2.p, h->Xl2.p, h->aux2.p);
+    CU_TRY(cudaGetLastError());
+    if ((rc = make_f16_map(&h->map2_hi, h->Lh.p, ld, ld, fk::KC, fk2::NB))) return rc;
+    if ((rc = make_f16_map(&h->map2_lo, h->Ll.p, ld, ld, fk::KC, fk2::NB))) return rc;
+    if ((rc = make_f16_map(&h->map2_xh, h->Xh2.p, 64, ld, 64, fk::KC))) return rc;
+    if ((rc = make_f16_map(&h->map2_xl, h->Xl2.p, 64, ld, 64, fk::KC))) return rc;
+  }
   CU_TRY(h->err_flag.reserve(1));
   CU_TRY(cudaMemsetAsync(h->err_flag.p, 0, sizeof(int), st));
   if (!h->copy_stream) {
@@ -822,6 +867,27 @@ static int ensure_fast_state(b200bo_handle h) {
 
 // one launch of the fused tensor-core kernel over m device-resident candidates; outputs at out_off
 static int launch_fused(b200bo_handle h, const double* xc_dev, long long m, size_t out_off) {
+  if (h->use_v2) {
+    fk2::Fused2Args a;
+    a.Xc = xc_dev; a.cscale = h->cscale.p; a.cmean = h->cmean.p; a.aux = h->aux2.p;
+    a.yhat = h->f_yhat.p + out_off; a.sumsq = h->f_sumsq.p + out_off; a.dotf = h->f_dotf.p + out_off;
+    a.exch = h->exch2.p;
+    a.dbg_w = h->want_dbg_w ? h->dbg_w.p : nullptr;
+    a.err = h->err_flag.p;
+    a.M = m; a.N = h->N; a.D = h->D; a.ld = h->ld; a.corr = h->corr; a.dk_steps = (h->D + 15) / 16; a.beta = h->beta;
+    a.out_scale = (float)ldexp(1.0, -(fk::A_SCALE_LOG2 + h->b_scale_log2));
+    const long long tiles = (m + fk::BM - 1) / fk::BM;
+    const int grid = (int)std::min<long long>(h->num_sms, tiles);
+    static bool attr2 = false;
+    if (!attr2) {
+      CU_TRY(cudaFuncSetAttribute(fk2::predict_fused_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fk2::SMEM_BYTES));
+      attr2 = true;
+    }
+    fk2::predict_fused_tc2_kernel<<<grid, fk2::NT2, fk2::SMEM_BYTES, h->stream>>>(h->map2_hi, h->map2_lo, h->map2_xh,
+                                                                                 h->map2_xl, a);
+    CU_TRY(cudaGetLastError());
+    return 0;
+  }
   fk::FusedArgs a;
   a.Xc = xc_dev; a.Xs = h->Xs.p; a.cscale = h->cscale.p;
   a.yhat = h->f_yhat.p + out_off; a.sumsq = h->f_sumsq.p + out_off; a.dotf = h->f_dotf.p + out_off;

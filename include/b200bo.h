@@ -91,6 +91,9 @@ int b200bo_destroy(b200bo_handle h);
 int b200bo_set_stream(b200bo_handle h, void* cuda_stream);
 int b200bo_set_precision(b200bo_handle h, int prec);
 int b200bo_set_keep_R(b200bo_handle h, int keep);
+/* which tensor-core kernel B200BO_PREC_FAST uses: 2 (default) = Gram product on the tensor cores where the kernel
+ * is a function of the L2 distance, else generation 1; 1 = always the first-generation kernel (A/B comparisons) */
+int b200bo_set_fast_kernel(b200bo_handle h, int generation);
 
 /* -- training data: GaussianProcess._check_data (gpr.py:279-310) --------------------------------------
  * X (N,D), y (N,) float64 host pointers.  The pairwise-distance pre-pass l1_cross_distances(X)
