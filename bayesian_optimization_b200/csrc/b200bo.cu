@@ -114,9 +114,9 @@ struct b200bo_ctx {
   int DP = 0, b_scale_log2 = 0;
   double dy_cal = 0, ds_cal = 0;
   DevBuf<__half> Lh, Ll;
-  DevBuf<float> Xs, band_hi, dbg_w;
-  DevBuf<double> cscale, fvec, f_yhat, f_sumsq, f_dotf, stage[2], thr, thr_part, Xband, errout;
-  DevBuf<long long> band_list;
+  DevBuf<float> Xs, dbg_w;
+  DevBuf<double> rs_part, cscale, fvec, f_yhat, f_sumsq, f_dotf, stage[2], Xband, errout, band_hiB;
+  DevBuf<long long> band_list, band_list0, thr_key;
   DevBuf<int> band_count, err_flag;
   CUtensorMap map_hi, map_lo;
   // second-generation kernel (Gram product on the tensor cores): its own operand copies
@@ -235,11 +235,12 @@ int b200bo_destroy(b200bo_handle h) {
   h->Xc.release(); h->Kst.release(); h->yhat.release(); h->sumsq.release(); h->dotf.release();
   h->mse.release(); h->params.release(); h->part_val.release(); h->best_val.release(); h->vals.release();
   h->part_idx.release(); h->best_idx.release();
-  h->Xh2.release(); h->Xl2.release(); h->aux2.release(); h->exch2.release(); h->cmean.release();
-  h->Lh.release(); h->Ll.release(); h->Xs.release(); h->band_hi.release(); h->dbg_w.release();
+  h->rs_part.release(); h->Xh2.release(); h->Xl2.release(); h->aux2.release(); h->exch2.release(); h->cmean.release();
+  h->Lh.release(); h->Ll.release(); h->Xs.release(); h->dbg_w.release();
   h->cscale.release(); h->fvec.release(); h->f_yhat.release(); h->f_sumsq.release(); h->f_dotf.release();
-  h->stage[0].release(); h->stage[1].release(); h->thr.release(); h->thr_part.release(); h->Xband.release();
-  h->errout.release(); h->band_list.release(); h->band_count.release(); h->err_flag.release();
+  h->stage[0].release(); h->stage[1].release(); h->Xband.release(); h->band_hiB.release();
+  h->errout.release(); h->band_list.release(); h->band_list0.release(); h->thr_key.release();
+  h->band_count.release(); h->err_flag.release();
   for (int i = 0; i < 2; ++i) {
     if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
     if (h->ev_used[i]) cudaEventDestroy(h->ev_used[i]);
@@ -606,6 +607,7 @@ int b200bo_get_state(b200bo_handle h, int what, double* out, size_t n_elems) {
 struct LaunchCount {
   int all = 0, contract = 0;
 };
+static const int RS_SMALL_MAX = 4096;  // candidates up to which the row-parallel contraction is used
 
 static int fp64_moments(b200bo_handle h, const double* xc_dev, int m, double* yh, int eval_mse, PhaseTimer* pt,
                         LaunchCount* lc) {
@@ -629,7 +631,21 @@ static int fp64_moments(b200bo_handle h, const double* xc_dev, int m, double* yh
   CU_TRY(cudaGetLastError());
   ++lc->all;
   if (pt) pt->end(0);
-  if (eval_mse) {
+  if (eval_mse && m <= RS_SMALL_MAX) {
+    // few candidates: one balanced sweep over the rows of L^-1 instead of one CTA per 128-candidate tile
+    if (pt) pt->begin(1);
+    const int nblk = ld / RS_ROWS, nctas = (nblk + 1) / 2, chunks = (m + RS_BC - 1) / RS_BC;
+    CU_TRY(h->rs_part.reserve((size_t)chunks * nctas * 2 * RS_BC));
+    RescoreArgs r;
+    r.Kst = h->Kst.p; r.Linv = h->W.p; r.Ft = h->Ft.p; r.part = h->rs_part.p; r.ld = ld; r.M = m;
+    rs_contract_kernel<<<dim3(nctas, chunks), 256, 0, st>>>(r);
+    CU_TRY(cudaGetLastError());
+    rs_reduce_kernel<<<(m + 127) / 128, 128, 0, st>>>(h->rs_part.p, nctas, m, h->sumsq.p, h->dotf.p);
+    CU_TRY(cudaGetLastError());
+    lc->all += 2;
+    ++lc->contract;
+    if (pt) pt->end(1);
+  } else if (eval_mse) {
     if (pt) pt->begin(1);
     ContractArgs c;
     c.Kst = h->Kst.p; c.Linv = h->W.p; c.Ft = h->Ft.p; c.sumsq = h->sumsq.p; c.dotf = h->dotf.p; c.ld = ld;
@@ -939,8 +955,6 @@ static int fast_errors(b200bo_handle h, const long long* list_dev, long long idx
 }
 
 static const int FAST_CHUNK_TILES = 8;        // candidate tiles per SM per fused launch when streaming from the host
-static const int BAND_CAP = 1 << 18;          // most candidates the exact re-score accepts before falling back
-static const int BAND_CHUNK = 1 << 20;        // candidates per band_bounds launch (bounds the q x chunk fp32 scratch)
 
 static int run_candidates_fast(b200bo_handle h, const double* Xc, int64_t M, int loc, int eval_mse, double* yhat_out,
                                double* mse_out, int acq_id, int minimize, double plugin, const double* params, int q,
@@ -1049,43 +1063,45 @@ static int run_candidates_fast(b200bo_handle h, const double* Xc, int64_t M, int
   }
 
   // ---- phase II / III: band selection, exact re-score; widen and repeat if the band shows larger errors --
-  CU_TRY(h->thr.reserve(q));
-  CU_TRY(h->band_list.reserve(BAND_CAP));
-  CU_TRY(h->band_count.reserve(1));
-  const int bchunk = (int)std::min<int64_t>(BAND_CHUNK, M);
-  CU_TRY(h->band_hi.reserve((size_t)q * bchunk));
-  const int nblk_b = std::min(h->num_sms * 2, (bchunk + 255) / 256);
-  CU_TRY(h->thr_part.reserve((size_t)q * nblk_b));
+  const int LIST0_CAP = 1 << 16;   // scan survivors (~ subsample stride x q when the criterion is not flat)
+  const int THR_STRIDE = 32;
+  CU_TRY(h->thr_key.reserve(2 * (size_t)q));
+  CU_TRY(h->band_list0.reserve(LIST0_CAP));
+  CU_TRY(h->band_list.reserve(LIST0_CAP));
+  CU_TRY(h->band_count.reserve(2));
+  CU_TRY(h->band_hiB.reserve((size_t)LIST0_CAP * q));
   CU_TRY(h->Xband.reserve((size_t)Mc * D));
   int rescored = 0, passes = 0;
   double dy = h->dy_cal, ds = h->ds_cal;
   std::vector<long long> list;
   for (;;) {
     ++passes;
-    std::vector<double> ninf(q, -INFINITY);
-    CU_TRY(cudaMemcpyAsync(h->thr.p, ninf.data(), q * 8, cudaMemcpyHostToDevice, st));
-    CU_TRY(cudaMemsetAsync(h->band_count.p, 0, sizeof(int), st));
+    std::vector<long long> ninf(2 * (size_t)q, fk::ord_key(-INFINITY));
+    CU_TRY(cudaMemcpyAsync(h->thr_key.p, ninf.data(), ninf.size() * 8, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemsetAsync(h->band_count.p, 0, 2 * sizeof(int), st));
+    CU_TRY(cudaStreamSynchronize(st));  // ninf is stack-owned
+    fk::BandArgs b;
+    b.yhat = h->f_yhat.p; b.sumsq = h->f_sumsq.p; b.dotf = h->f_dotf.p; b.params = h->params.p;
+    b.M = M; b.acq = acq_id; b.minimize = minimize; b.estimate_trend = h->estimate_trend; b.q = q;
+    b.sigma2 = h->sigma2; b.plugin = plugin; b.G = h->G; b.dy = dy; b.ds = ds;
+    const long long ns = (M + THR_STRIDE - 1) / THR_STRIDE;
+    fk::band_thr0_kernel<<<(int)std::min<long long>(h->num_sms * 4, (ns + 255) / 256), 256, 0, st>>>(b, THR_STRIDE, h->thr_key.p);
+    CU_TRY(cudaGetLastError());
+    fk::band_scan_kernel<<<(int)std::min<long long>(h->num_sms * 8, (M + 255) / 256), 256, 0, st>>>(
+        b, h->thr_key.p, h->band_list0.p, LIST0_CAP, h->band_count.p);
+    CU_TRY(cudaGetLastError());
+    fk::band_refine_kernel<<<h->num_sms, 256, 0, st>>>(b, h->band_list0.p, h->band_count.p, LIST0_CAP, h->band_hiB.p,
+                                                       h->thr_key.p + q);
+    CU_TRY(cudaGetLastError());
+    fk::band_filter_kernel<<<h->num_sms, 256, 0, st>>>(h->band_list0.p, h->band_count.p, LIST0_CAP, h->band_hiB.p,
+                                                       h->thr_key.p + q, q, h->band_list.p, h->band_count.p + 1);
+    CU_TRY(cudaGetLastError());
+    lc.all += 4;
+    int counts[2] = {0, 0};
+    CU_TRY(cudaMemcpyAsync(counts, h->band_count.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
-    for (int64_t a = 0; a < M; a += bchunk) {
-      const int m = (int)std::min<int64_t>(bchunk, M - a);
-      fk::BandArgs b;
-      b.yhat = h->f_yhat.p + a; b.sumsq = h->f_sumsq.p + a; b.dotf = h->f_dotf.p + a; b.params = h->params.p;
-      b.hi = h->band_hi.p; b.thr_part = h->thr_part.p;
-      b.M = m; b.acq = acq_id; b.minimize = minimize; b.estimate_trend = h->estimate_trend; b.q = q;
-      b.sigma2 = h->sigma2; b.plugin = plugin; b.G = h->G; b.dy = dy; b.ds = ds;
-      const int nb = std::min(h->num_sms * 2, (m + 255) / 256);
-      fk::band_bounds_kernel<<<dim3(nb, q), 256, 0, st>>>(b);
-      CU_TRY(cudaGetLastError());
-      fk::band_thr_merge_kernel<<<(q + 63) / 64, 64, 0, st>>>(h->thr_part.p, nb, q, h->thr.p);
-      CU_TRY(cudaGetLastError());
-      fk::band_flag_kernel<<<nb, 256, 0, st>>>(h->band_hi.p, h->thr.p, m, q, a, h->band_list.p, BAND_CAP, h->band_count.p);
-      CU_TRY(cudaGetLastError());
-      lc.all += 3;
-    }
-    int count = 0;
-    CU_TRY(cudaMemcpyAsync(&count, h->band_count.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CU_TRY(cudaStreamSynchronize(st));
-    if (count > BAND_CAP || passes > 4) {  // degenerate (flat criterion) or unstable error estimate
+    const int count = counts[1];
+    if (counts[0] > LIST0_CAP || passes > 4) {  // degenerate (flat criterion) or unstable error estimate
       *fell_back = true;
       return 0;
     }
@@ -1139,7 +1155,7 @@ static int run_candidates(b200bo_handle h, const double* Xc, int64_t M, int loc,
   CHECK_ARG(loc == B200BO_HOST || loc == B200BO_DEVICE, "bad loc");
   CU_TRY(cudaSetDevice(h->device));
   // the tensor-core pass needs the variance (its product is rt) and cannot return all q x M values exactly
-  if (h->prec == B200BO_PREC_FAST && fast_supported(h) && eval_mse && !vals && M > 0) {
+  if (h->prec == B200BO_PREC_FAST && fast_supported(h) && eval_mse && !vals && M > 0 && q <= fk::BAND_MAX_Q) {
     bool fell_back = false;
     int rc = run_candidates_fast(h, Xc, M, loc, eval_mse, yhat_out, mse_out, acq_id, minimize, plugin, params, q,
                                  best_val, best_idx, &fell_back);

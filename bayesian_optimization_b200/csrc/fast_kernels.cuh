@@ -499,83 +499,244 @@ __global__ void xs_prep_kernel(const double* __restrict__ Xt, const double* __re
 }
 
 // ------------------------------------------------------------------------------------------------------
-// arg-max band: which candidates could still be the maximiser once the fast pass's error is allowed for
+// arg-max band: which candidates could still be the maximiser once the fast pass's error is allowed for.
+//
+// Every candidate carries a box [y - dy, y + dy] x [mse - ds, mse + ds] around its fast moments.  A criterion's
+// lower / upper bound over the box follows from monotonicity (EI, PI, MGFI decrease with the signed mean; EI and UCB
+// increase with s; PI and MGFI are evaluated at the s-end their numerator's sign selects, or at both ends).
+//   1. band_thr0_kernel   : thr0_c = max lower bound over a strided SUBSAMPLE -- any lower bound of the true
+//                           maximum is a valid threshold
+//   2. band_scan_kernel   : all candidates; upper bound first in fp32 (directed-rounded box, explicit margins), in
+//                           fp64 only when the fp32 screen cannot reject; survivors -> list0 (~ stride x q entries)
+//   3. band_refine_kernel : exact bounds for list0; thr1_c = max lower bound (list0 contains the global best)
+//   4. band_filter_kernel : list0 entries whose upper bound reaches thr1_c for some criterion -> the band
 // ------------------------------------------------------------------------------------------------------
 struct BandArgs {
   const double* yhat;    // (M,) fast
   const double* sumsq;   // (M,)
   const double* dotf;    // (M,)
   const double* params;  // (q,)
-  float* hi;             // (q, M) upper bounds, rounded up
-  double* thr_part;      // (q, gridDim.x) block maxima of the lower bounds
-  int M, acq, minimize, estimate_trend, q;
+  long long M;
+  int acq, minimize, estimate_trend, q;
   double sigma2, plugin, G;
   double dy, ds;  // half-widths of the error intervals of yhat and mse
 };
 
-__device__ __forceinline__ double fast_mse(const BandArgs& p, int i) {
+struct Box {
+  double ylo, yhi, s0, s1;  // signed mean (negated when maximising) and standard deviation, both ends
+};
+
+__device__ __forceinline__ Box band_box(const BandArgs& p, long long i) {
   double u2 = 0.0;
   if (p.estimate_trend) {
     const double u = (p.dotf[i] - 1.0) / p.G;
     u2 = u * u;
   }
-  return (1.0 - p.sumsq[i] + u2) * p.sigma2;  // unclipped: the interval is clipped below
+  const double mse = (1.0 - p.sumsq[i] + u2) * p.sigma2;  // unclipped; the interval ends are clipped (gpr.py:510)
+  const double y = p.minimize ? p.yhat[i] : -p.yhat[i];
+  Box b;
+  b.ylo = y - p.dy;
+  b.yhi = y + p.dy;
+  b.s0 = sqrt(fmax(mse - p.ds, 0.0));
+  b.s1 = sqrt(fmax(mse + p.ds, 0.0));
+  return b;
 }
 
-// lower / upper bound of the criterion over [y - dy, y + dy] x [mse - ds, mse + ds]: all four criteria are
-// monotone in yhat for fixed s; in s they are evaluated at both ends (EI, UCB are monotone in s as well)
-__device__ __forceinline__ void acq_bounds(int acq, double y, double mse, double dy, double ds, double sigma2,
-                                           double plugin, double par, int minimize, double& lo, double& hi) {
-  const double m0 = fmax(mse - ds, 0.0), m1 = fmax(mse + ds, 0.0);
-  // acq_value negates yhat when maximising; in both cases the criterion decreases with the (signed) mean
-  // for EI / PI / MGFI and increases for UCB -- evaluate all four corners, it is only ~4x a single value
-  const double a = acq_value(acq, y - dy, m0, sigma2, plugin, par, minimize);
-  const double b = acq_value(acq, y - dy, m1, sigma2, plugin, par, minimize);
-  const double c = acq_value(acq, y + dy, m0, sigma2, plugin, par, minimize);
-  const double d = acq_value(acq, y + dy, m1, sigma2, plugin, par, minimize);
-  lo = fmin(fmin(a, b), fmin(c, d));
-  hi = fmax(fmax(a, b), fmax(c, d));
-}
+__device__ __forceinline__ double pi_coef(double y, double eps) { return y > 0 ? 1.0 - eps : 1.0 + eps; }
 
-__global__ void __launch_bounds__(256) band_bounds_kernel(BandArgs p) {
-  __shared__ double sv[8];
-  const int c = blockIdx.y;
-  const double par = p.acq == ACQ_MGFI ? fmin(p.params[c], 22.36) : p.params[c];
-  double best = -INFINITY;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.M; i += gridDim.x * blockDim.x) {
-    double lo, hi;
-    acq_bounds(p.acq, p.yhat[i], fast_mse(p, i), p.dy, p.ds, p.sigma2, p.plugin, par, p.minimize, lo, hi);
-    p.hi[(size_t)c * p.M + i] = hi != hi ? INFINITY : __double2float_ru(hi);
-    if (lo == lo) best = fmax(best, lo);
+__device__ __forceinline__ double band_hi(const BandArgs& p, const Box& b, double par) {
+  double v;
+  switch (p.acq) {
+    case ACQ_EI:
+      v = acq_ei(b.ylo, b.s1, p.sigma2, p.plugin);
+      break;
+    case ACQ_UCB:
+      v = acq_ucb(b.yhi, b.s1, par);
+      break;
+    case ACQ_PI:
+      if (par < 1.0) {
+        v = acq_pi(b.ylo, (p.plugin - pi_coef(b.ylo, par) * b.ylo) >= 0 ? b.s0 : b.s1, p.plugin, par);
+      } else {
+        v = fmax(fmax(acq_pi(b.ylo, b.s0, p.plugin, par), acq_pi(b.ylo, b.s1, p.plugin, par)),
+                 fmax(acq_pi(b.yhi, b.s0, p.plugin, par), acq_pi(b.yhi, b.s1, p.plugin, par)));
+      }
+      break;
+    default: {  // MGFI
+      if (par * (p.plugin - b.ylo - 1.0) + par * par * b.s1 * b.s1 / 2.0 > 700.0) return INFINITY;  // exp overflow -> 0 quirk
+      v = acq_mgfi(b.ylo, b.s1, p.plugin, par);
+      if (p.plugin - b.ylo > 0) v = fmax(v, acq_mgfi(b.ylo, b.s0, p.plugin, par));
+    }
   }
-  for (int o = 16; o; o >>= 1) best = fmax(best, __shfl_xor_sync(0xffffffffu, best, o));
-  if ((threadIdx.x & 31) == 0) sv[threadIdx.x >> 5] = best;
+  if (v != v) return INFINITY;
+  return v + 1e-12 * fabs(v);
+}
+
+__device__ __forceinline__ double band_lo(const BandArgs& p, const Box& b, double par) {
+  double v;
+  switch (p.acq) {
+    case ACQ_EI:
+      v = acq_ei(b.yhi, b.s0, p.sigma2, p.plugin);
+      break;
+    case ACQ_UCB:
+      v = acq_ucb(b.ylo, b.s0, par);
+      break;
+    case ACQ_PI:
+      if (par < 1.0) {
+        v = acq_pi(b.yhi, (p.plugin - pi_coef(b.yhi, par) * b.yhi) >= 0 ? b.s1 : b.s0, p.plugin, par);
+      } else {
+        v = fmin(fmin(acq_pi(b.ylo, b.s0, p.plugin, par), acq_pi(b.ylo, b.s1, p.plugin, par)),
+                 fmin(acq_pi(b.yhi, b.s0, p.plugin, par), acq_pi(b.yhi, b.s1, p.plugin, par)));
+      }
+      break;
+    default: {
+      v = acq_mgfi(b.yhi, b.s0, p.plugin, par);
+      if (p.plugin - b.yhi > 0) v = fmin(v, acq_mgfi(b.yhi, b.s1, p.plugin, par));
+    }
+  }
+  if (v != v) return -INFINITY;
+  return v - 1e-12 * fabs(v);
+}
+
+// fp32 over-estimate of band_hi (or +inf when fp32 cannot decide).  The box is rounded outwards, every product
+// formula gets a relative margin far above fp32 rounding, EI an absolute margin for its cancellation.
+__device__ __forceinline__ float norm_cdf_f(float z) { return 0.5f * erfcf(-z * 0.70710678f); }
+__device__ __forceinline__ float band_hi_f32(int acq, float ylo, float s0, float s1, float plugin, float par,
+                                            float inv_sqrt_sigma2) {
+  if (acq == ACQ_EI) {
+    if (s1 * inv_sqrt_sigma2 < 0.99e-6f) return 0.f;  // acq_ei's early-out, with slack
+    const float d = plugin - ylo, z = d / s1;
+    const float a = d * norm_cdf_f(z), b = s1 * 0.39894228f * __expf(-0.5f * z * z);
+    return a + b + 2e-6f * (fabsf(a) + b);
+  }
+  if (acq == ACQ_PI) {
+    const float coef = ylo > 0 ? 1.0f - par : 1.0f + par;
+    const float num = plugin - coef * ylo;
+    const float sd = num >= 0 ? s0 : s1;
+    if (!(sd > 0.f)) return INFINITY;
+    return norm_cdf_f(num / sd + 1e-5f * fabsf(num / sd) + 1e-6f) * 1.0001f;
+  }
+  // MGFI (par already capped at 22.36); the caller handles the plugin - ylo > 0 branch in fp64
+  const float e = par * (plugin - ylo - 1.0f) + 0.5f * par * par * s1 * s1;
+  if (e > 80.f) return INFINITY;
+  const float bp = (plugin - ylo) / s1 + par * s1;
+  return norm_cdf_f(bp + 1e-5f * fabsf(bp) + 1e-6f) * __expf(e + 1e-5f * fabsf(e) + 1e-6f) * 1.0001f;
+}
+
+// monotone map double -> signed 64-bit key, so atomicMax on the key is a max on the value
+__host__ __device__ __forceinline__ long long ord_key(double v) {
+#if defined(__CUDA_ARCH__)
+  long long k = __double_as_longlong(v);
+#else
+  long long k;
+  memcpy(&k, &v, 8);
+#endif
+  return k >= 0 ? k : k ^ 0x7FFFFFFFFFFFFFFFLL;
+}
+__host__ __device__ __forceinline__ double ord_val(long long k) {
+  k = k >= 0 ? k : k ^ 0x7FFFFFFFFFFFFFFFLL;
+#if defined(__CUDA_ARCH__)
+  return __longlong_as_double(k);
+#else
+  double v;
+  memcpy(&v, &k, 8);
+  return v;
+#endif
+}
+
+constexpr int BAND_MAX_Q = 512;  // criteria per call on the band path (parameters live in shared memory)
+
+__device__ __forceinline__ double band_par(const BandArgs& p, int c) {
+  return p.acq == ACQ_MGFI ? fmin(p.params[c], 22.36) : p.params[c];  // acquisition_fun.py:262
+}
+
+// 1. threshold from a strided subsample: thr_key[c] = max_c lower bound
+__global__ void __launch_bounds__(256) band_thr0_kernel(BandArgs p, int stride, long long* __restrict__ thr_key) {
+  __shared__ double par_s[BAND_MAX_Q];
+  for (int c = threadIdx.x; c < p.q; c += blockDim.x) par_s[c] = band_par(p, c);
   __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int k = 1; k < 8; ++k) best = fmax(best, sv[k]);
-    p.thr_part[(size_t)c * gridDim.x + blockIdx.x] = best;
+  const long long ns = (p.M + stride - 1) / stride;
+  for (long long k0 = (long long)blockIdx.x * blockDim.x; k0 < ns; k0 += (long long)gridDim.x * blockDim.x) {
+    const long long k = k0 + threadIdx.x;
+    const bool on = k < ns;
+    Box b;
+    if (on) b = band_box(p, k * stride);
+    for (int c = 0; c < p.q; ++c) {
+      double lo = on ? band_lo(p, b, par_s[c]) : -INFINITY;
+      for (int o = 16; o; o >>= 1) lo = fmax(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+      if ((threadIdx.x & 31) == 0 && lo > -INFINITY) atomicMax(thr_key + c, ord_key(lo));
+    }
   }
 }
 
-// thr[c] <- max(thr[c], block partials)
-__global__ void band_thr_merge_kernel(const double* __restrict__ part, int nblocks, int q, double* __restrict__ thr) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= q) return;
-  double t = thr[c];
-  for (int b = 0; b < nblocks; ++b) t = fmax(t, part[(size_t)c * nblocks + b]);
-  thr[c] = t;
-}
-
-// append (global index) of every candidate whose upper bound reaches the threshold of any criterion
-__global__ void band_flag_kernel(const float* __restrict__ hi, const double* __restrict__ thr, int M, int q,
-                                 long long idx_base, long long* __restrict__ list, int cap, int* __restrict__ count) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < M; i += gridDim.x * blockDim.x) {
+// 2. scan: candidates whose upper bound reaches thr0 for some criterion -> list (positions >= cap are dropped and
+//    reported through the count)
+__global__ void __launch_bounds__(256) band_scan_kernel(BandArgs p, const long long* __restrict__ thr_key,
+                                                        long long* __restrict__ list, int cap, int* __restrict__ count) {
+  __shared__ double par_s[BAND_MAX_Q], thr_s[BAND_MAX_Q];
+  for (int c = threadIdx.x; c < p.q; c += blockDim.x) {
+    par_s[c] = band_par(p, c);
+    thr_s[c] = ord_val(thr_key[c]);
+  }
+  __syncthreads();
+  const float plf = (float)p.plugin, iss = (float)(1.0 / sqrt(p.sigma2));
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.M; i += (long long)gridDim.x * blockDim.x) {
+    const Box b = band_box(p, i);
+    const float ylo = __double2float_rd(b.ylo), s0 = __double2float_rd(b.s0), s1 = __double2float_ru(b.s1);
     bool in = false;
-    for (int c = 0; c < q && !in; ++c) in = (double)hi[(size_t)c * M + i] >= thr[c];
+    for (int c = 0; c < p.q && !in; ++c) {
+      const double thr = thr_s[c];
+      if (p.acq == ACQ_UCB) {
+        in = band_hi(p, b, par_s[c]) >= thr;
+        continue;
+      }
+      // fp32 screen only where fp32 resolves the threshold (far from underflow) and the criterion is monotone in s
+      const bool screen = thr > 1e-20 && thr < 1e30 && !(p.acq == ACQ_MGFI && p.plugin - b.ylo > 0) &&
+                          !(p.acq == ACQ_PI && par_s[c] >= 1.0);
+      if (screen && (double)band_hi_f32(p.acq, ylo, s0, s1, plf, (float)par_s[c], iss) < thr) continue;
+      in = band_hi(p, b, par_s[c]) >= thr;
+    }
     if (in) {
       const int pos = atomicAdd(count, 1);
-      if (pos < cap) list[pos] = idx_base + i;
+      if (pos < cap) list[pos] = i;
     }
+  }
+}
+
+// 3. exact bounds of the listed candidates: hiB (n, q) and thr1_key[c] = max lower bound
+__global__ void __launch_bounds__(256) band_refine_kernel(BandArgs p, const long long* __restrict__ list,
+                                                          const int* __restrict__ count, int cap,
+                                                          double* __restrict__ hiB, long long* __restrict__ thr_key) {
+  __shared__ double par_s[BAND_MAX_Q];
+  for (int c = threadIdx.x; c < p.q; c += blockDim.x) par_s[c] = band_par(p, c);
+  __syncthreads();
+  const int n = min(*count, cap);
+  for (int b0 = blockIdx.x * blockDim.x; b0 < n; b0 += gridDim.x * blockDim.x) {
+    const int bi = b0 + threadIdx.x;
+    const bool on = bi < n;
+    Box b;
+    if (on) b = band_box(p, list[bi]);
+    for (int c = 0; c < p.q; ++c) {
+      double lo = -INFINITY;
+      if (on) {
+        lo = band_lo(p, b, par_s[c]);
+        hiB[(size_t)bi * p.q + c] = band_hi(p, b, par_s[c]);
+      }
+      for (int o = 16; o; o >>= 1) lo = fmax(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+      if ((threadIdx.x & 31) == 0 && lo > -INFINITY) atomicMax(thr_key + c, ord_key(lo));
+    }
+  }
+}
+
+// 4. the band: listed candidates that reach the refined threshold of some criterion
+__global__ void __launch_bounds__(256) band_filter_kernel(const long long* __restrict__ list, const int* __restrict__ count,
+                                                          int cap, const double* __restrict__ hiB,
+                                                          const long long* __restrict__ thr_key, int q,
+                                                          long long* __restrict__ out, int* __restrict__ out_count) {
+  const int n = min(*count, cap);
+  for (int bi = blockIdx.x * blockDim.x + threadIdx.x; bi < n; bi += gridDim.x * blockDim.x) {
+    bool in = false;
+    for (int c = 0; c < q && !in; ++c) in = hiB[(size_t)bi * q + c] >= ord_val(thr_key[c]);
+    if (in) out[atomicAdd(out_count, 1)] = list[bi];
   }
 }
 

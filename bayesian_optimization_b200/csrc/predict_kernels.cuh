@@ -160,6 +160,91 @@ __global__ void __launch_bounds__(PredCore::NT, 1) contract_fp64_kernel(Contract
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Small-M flavour of the same contraction (M <= a few thousand: the reference's own calling pattern is M = 1,
+// acquisition_fun.py:52-64, and the fast path re-scores a handful of band candidates).  With few candidates
+// the work is one sweep over the lower triangle of L^-1, so it is parallelised over ROW blocks of L^-1
+// instead of candidate tiles: CTA c owns the 32-row blocks c and nblk-1-c (balanced triangle), 32 candidates
+// at a time, and writes per-CTA partial sums that rs_reduce_kernel adds in a fixed order (deterministic).
+// ---------------------------------------------------------------------------------------------------
+constexpr int RS_ROWS = 32, RS_KT = 64, RS_BC = 32, RS_LD = RS_KT + 1;
+
+struct RescoreArgs {
+  const double* Kst;   // (Mpad, ld) rows of r
+  const double* Linv;  // (ld, ld) lower, zeros above the diagonal
+  const double* Ft;    // (ld,)
+  double* part;        // (chunks, gridDim.x, 2, RS_BC) partial sums: [0] sum rt^2, [1] Ft . rt
+  int ld, M;
+};
+
+__global__ void __launch_bounds__(256) rs_contract_kernel(RescoreArgs p) {
+  __shared__ double buf[2][RS_ROWS][RS_LD];
+  double (*Ls)[RS_LD] = buf[0];
+  double (*Ks)[RS_LD] = buf[1];
+  double (*red)[RS_ROWS][RS_BC + 1] = (double (*)[RS_ROWS][RS_BC + 1]) & buf[0][0][0];  // reused after the k sweep
+  const int tid = threadIdx.x;
+  const int nl = tid >> 3, bg = tid & 7;  // row of the block, group of 4 candidates
+  const int nblk = p.ld / RS_ROWS;
+  const int cand0 = blockIdx.y * RS_BC;
+  double tot_ss = 0.0, tot_df = 0.0;  // threads 0..31: totals of candidate tid
+  for (int half = 0; half < 2; ++half) {
+    const int rb = half == 0 ? (int)blockIdx.x : nblk - 1 - (int)blockIdx.x;
+    if (rb >= nblk || rb < 0 || (half == 1 && rb <= (int)blockIdx.x)) continue;
+    const int n0 = rb * RS_ROWS;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int k0 = 0; k0 < n0 + RS_ROWS; k0 += RS_KT) {
+      for (int e = tid; e < RS_ROWS * RS_KT; e += 256) {
+        const int r = e / RS_KT, c = e % RS_KT;
+        Ls[r][c] = p.Linv[(size_t)(n0 + r) * p.ld + k0 + c];
+        Ks[r][c] = (cand0 + r < p.M) ? p.Kst[(size_t)(cand0 + r) * p.ld + k0 + c] : 0.0;
+      }
+      __syncthreads();
+#pragma unroll 8
+      for (int kk = 0; kk < RS_KT; ++kk) {
+        const double l = Ls[nl][kk];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] += l * Ks[bg * 4 + j][kk];
+      }
+      __syncthreads();
+    }
+    const double f = p.Ft[n0 + nl];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      red[0][nl][bg * 4 + j] = acc[j] * acc[j];
+      red[1][nl][bg * 4 + j] = f * acc[j];
+    }
+    __syncthreads();
+    if (tid < RS_BC) {
+#pragma unroll 4
+      for (int r = 0; r < RS_ROWS; ++r) {
+        tot_ss += red[0][r][tid];
+        tot_df += red[1][r][tid];
+      }
+    }
+    __syncthreads();
+  }
+  if (tid < RS_BC) {
+    double* o = p.part + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 2 * RS_BC;
+    o[tid] = tot_ss;
+    o[RS_BC + tid] = tot_df;
+  }
+}
+
+__global__ void rs_reduce_kernel(const double* __restrict__ part, int nctas, int M, double* __restrict__ sumsq,
+                                 double* __restrict__ dotf) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  const int chunk = i / RS_BC, b = i % RS_BC;
+  double a = 0.0, d = 0.0;
+  for (int c = 0; c < nctas; ++c) {
+    const double* o = part + ((size_t)chunk * nctas + c) * 2 * RS_BC;
+    a += o[b];
+    d += o[RS_BC + b];
+  }
+  sumsq[i] = a;
+  dotf[i] = d;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // MSE + acquisition + block arg-max.  grid = (candidate blocks, q criteria).
 // ---------------------------------------------------------------------------------------------------
 struct AcqArgs {

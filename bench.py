@@ -274,19 +274,23 @@ def run_b200(args, w, params):
         "hbm_frac": value / world * (8 * w.D) / 1e9 / peaks.get("hbm_gbs", 6550.0),
     }
     if fast:
-        # executed tensor work: 3 fp16 products per algorithmic MAC over the 512-wide super-tiles (blocks above the
-        # diagonal skipped at 256-column granularity)
+        # executed tensor work per candidate: 3 fp16 products per MAC over the accumulator super-tiles, blocks above
+        # the diagonal skipped at the kernel's granularity; generation 2 adds the Gram MMAs (64 x 16 ceil(D/16) per chunk)
         ld = -(-w.N // 128) * 128
+        gen2 = w.corr != "absolute_exponential"
+        WC_, NB_ = (384, 128) if gen2 else (512, 256)
         mac = 0
-        for s_ in range(-(-ld // 512)):
-            kext = min(ld, 512 * (s_ + 1))
-            for hf in range(2):
-                n0 = 512 * s_ + 256 * hf
+        for s_ in range(-(-ld // WC_)):
+            kext = min(ld, WC_ * (s_ + 1))
+            for j_ in range(WC_ // NB_):
+                n0 = WC_ * s_ + NB_ * j_
                 if n0 < ld:
-                    mac += 256 * min(kext, n0 + 256)
+                    mac += NB_ * min(kext, -(-(n0 + NB_) // 64) * 64)
+            if gen2:
+                mac += (kext // 64) * 64 * 16 * (-(-w.D // 16))
         exe = cand_per_launch * 3 * 2.0 * mac / (launch_ms * 1e-3) / 1e12
         roofline.update({
-            "kernel": "predict_fused_tc_kernel (tcgen05.mma kind::f16, 3 split-fp16 products per MAC, fp32 TMEM accumulators)",
+            "kernel": ("predict_fused_tc2_kernel" if gen2 else "predict_fused_tc_kernel") + " (tcgen05.mma kind::f16, 3 split-fp16 products per MAC, fp32 TMEM accumulators)",
             "executed_tensor_tflops": exe, "executed_frac": exe / peak,
             "note": "achieved counts ALGORITHMIC flops (N^2 per candidate); the split scheme executes ~3.4x that on the "
                     "tensor pipe, so frac <= ~0.3 by construction; executed_frac is the tensor-pipe utilisation",

@@ -93,11 +93,12 @@ def test_fast_argmax_is_exact(N, D, corr, corr_id, acq, params):
         vo = go.acquisition(acq, yo, mo, ora.sigma2, pl, par, True)
         assert int(bi[k]) == int(np.argmax(vo)), (k, par, bi[k], int(np.argmax(vo)), t)
         assert bv[k] == pytest.approx(vo.max(), rel=1e-7, abs=1e-300)
-    # the fp64 path gives the same answer bit for bit (the re-score IS the fp64 path)
+    # the fp64 path gives the same answer (the re-score IS fp64 arithmetic; the summation order of the small-M
+    # contraction differs from the tiled one, hence 1e-12 and not bit equality)
     eng.set_precision(_lib.PREC_FP64)
     bv2, bi2, _ = eng.acq(Xc, acq, True, pl, params)
     np.testing.assert_array_equal(bi, bi2)
-    np.testing.assert_array_equal(bv, bv2)
+    np.testing.assert_allclose(bv, bv2, rtol=1e-11, atol=1e-300)
 
 
 def test_fast_device_resident_and_maximize():
@@ -114,7 +115,7 @@ def test_fast_device_resident_and_maximize():
     eng.set_precision(_lib.PREC_FAST)
     xd = torch.from_numpy(Xc).cuda()
     got = eng.acq(xd, _lib.ACQ_EI, False, pl, [0.0])
-    assert int(got[1][0]) == int(ref[1][0]) and got[0][0] == ref[0][0]
+    assert int(got[1][0]) == int(ref[1][0]) and got[0][0] == pytest.approx(ref[0][0], rel=1e-11)
 
 
 def test_fast_flat_criterion_falls_back():
@@ -127,4 +128,4 @@ def test_fast_flat_criterion_falls_back():
     bv, bi, _ = eng.acq(Xc, _lib.ACQ_EI, True, -1e6, [0.0])
     eng.set_precision(_lib.PREC_FP64)
     bv2, bi2, _ = eng.acq(Xc, _lib.ACQ_EI, True, -1e6, [0.0])
-    assert int(bi[0]) == int(bi2[0]) and bv[0] == bv2[0]
+    assert int(bi[0]) == int(bi2[0]) and bv[0] == pytest.approx(bv2[0], rel=1e-11, abs=1e-300)
