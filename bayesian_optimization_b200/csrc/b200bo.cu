@@ -894,13 +894,19 @@ static int launch_fused(b200bo_handle h, const double* xc_dev, long long m, size
     a.out_scale = (float)ldexp(1.0, -(fk::A_SCALE_LOG2 + h->b_scale_log2));
     const long long tiles = (m + fk::BM - 1) / fk::BM;
     const int grid = (int)std::min<long long>(h->num_sms, tiles);
-    static bool attr2 = false;
-    if (!attr2) {
-      CU_TRY(cudaFuncSetAttribute(fk2::predict_fused_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fk2::SMEM_BYTES));
-      attr2 = true;
+#define FK2_LAUNCH(C)                                                                                               \
+  do {                                                                                                             \
+    auto kern = fk2::predict_fused_tc2_kernel<C>;                                                                  \
+    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fk2::SMEM_BYTES));              \
+    kern<<<grid, fk2::NT2, fk2::SMEM_BYTES, h->stream>>>(h->map2_hi, h->map2_lo, h->map2_xh, h->map2_xl, a);        \
+  } while (0)
+    switch (h->corr) {
+      case RBF: FK2_LAUNCH(RBF); break;
+      case MATERN12: FK2_LAUNCH(MATERN12); break;
+      case MATERN32: FK2_LAUNCH(MATERN32); break;
+      default: FK2_LAUNCH(MATERN52); break;
     }
-    fk2::predict_fused_tc2_kernel<<<grid, fk2::NT2, fk2::SMEM_BYTES, h->stream>>>(h->map2_hi, h->map2_lo, h->map2_xh,
-                                                                                 h->map2_xl, a);
+#undef FK2_LAUNCH
     CU_TRY(cudaGetLastError());
     return 0;
   }

@@ -92,6 +92,18 @@ enum {
   BAR_ACC_EMPTY = 18 // epilogue -> MMA (count 4)
 };
 
+// r * 2^14 from the (clamped) scaled squared distance; CORR is a template parameter so the loop body is branch-free
+template <int CORR>
+__device__ __forceinline__ float corr_from_acc(float acc) {
+  if (CORR == RBF) return ex2_approx((float)A_SCALE_LOG2 - acc);
+  const float t = sqrt_approx(acc);
+  const float e = ex2_approx(fmaf(t, -1.4426950408889634f, (float)A_SCALE_LOG2));
+  if (CORR == MATERN12) return e;
+  if (CORR == MATERN32) return fmaf(t, e, e);
+  return fmaf(acc, 1.0f / 3.0f, 1.0f + t) * e;  // MATERN52
+}
+
+template <int CORR>
 __global__ void __launch_bounds__(NT2, 1)
 predict_fused_tc2_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
                          const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
@@ -296,7 +308,6 @@ predict_fused_tc2_kernel(const __grid_constant__ CUtensorMap map_hi, const __gri
     const uint32_t row_off = (uint32_t)((m >> 3) * 1024 + (m & 7) * 128);
     float2* exch = p.exch + (size_t)blockIdx.x * 3 * BM;  // [3][128] partial dot products of quarters 1..3
     const float CG = -2.0f / (float)(1 << (2 * X_SCALE_LOG2));
-    const float LOG2E = 1.4426950408889634f;
     uint32_t ic = 0;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       // ---- candidate operand of the Gram MMA: this thread writes 32 B (16 features) of its row, hi and lo ----
@@ -362,17 +373,8 @@ predict_fused_tc2_kernel(const __grid_constant__ CUtensorMap map_hi, const __gri
           float kv[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            float acc = fmaf(CG, __uint_as_float(gr[i]), am + bj[i]);
-            acc = fmaxf(acc, 0.f);
-            float v;
-            if (p.corr == RBF) {
-              v = ex2_approx((float)A_SCALE_LOG2 - acc);
-            } else {
-              const float t = acc * rsqrtf(fmaxf(acc, 1e-30f));
-              const float e = ex2_approx((float)A_SCALE_LOG2 - t * LOG2E);
-              v = p.corr == MATERN12 ? e : p.corr == MATERN32 ? fmaf(t, e, e) : (1.0f + t + acc * (1.0f / 3.0f)) * e;
-            }
-            kv[i] = v;
+            const float acc = fmaxf(fmaf(CG, __uint_as_float(gr[i]), am + bj[i]), 0.f);
+            kv[i] = corr_from_acc<CORR>(acc);
           }
           if (last) {
 #pragma unroll

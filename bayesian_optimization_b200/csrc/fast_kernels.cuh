@@ -44,7 +44,8 @@ constexpr int PRODUCER_WARP0 = 8;                  // warps 8..15
 constexpr int EPI_WARP0 = 4;                       // warps 4..7 (warp % 4 = TMEM lane quadrant)
 constexpr int NT = 32 * (PRODUCER_WARP0 + NUM_PRODUCER_WARPS);  // 512 threads
 constexpr int A_SCALE_LOG2 = 14;                   // r in [0,1] -> [0, 2^14] before the fp16 split
-constexpr long long WAIT_TIMEOUT_CYCLES = 4000000000LL;
+constexpr uint32_t WAIT_MAX_SPINS = 1u << 24;
+constexpr long long WAIT_TIMEOUT_CYCLES = 8000000000LL;  // ~4-5 s: a pipeline bug traps instead of hanging the GPU
 
 __host__ __device__ constexpr int smem_off_A(int s) { return s * A_STAGE_BYTES; }
 __host__ __device__ constexpr int smem_off_B(int s) { return A_STAGES * A_STAGE_BYTES + s * B_STAGE_BYTES; }
@@ -93,15 +94,33 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
       : "memory");
   return ok;
 }
-// bounded wait: a pipeline bug must not hang the GPU -- flag it and trap
+// try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes (woken by the arrive)
+// or the hint expires -- no instruction issue while waiting, which matters under the 1 kW power cap
+__device__ __forceinline__ uint32_t mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t hint_ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(hint_ns)
+      : "memory");
+  return ok;
+}
+// bounded wait: a pipeline bug must not hang the GPU -- flag it and trap (~2 s: 2^17 sleeps of <= 16 us)
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err, int code) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > WAIT_TIMEOUT_CYCLES) {
-      atomicExch(err, code);
-      __threadfence_system();
-      __trap();
+  uint32_t spins = 0;
+  long long t0 = 0;
+  while (!mbar_try_wait_hint(bar, parity, 16000u)) {
+    if ((++spins & 63u) == 0) {  // look at the clock only now and then
+      const long long t = clock64();
+      if (t0 == 0) t0 = t;
+      if (t - t0 > WAIT_TIMEOUT_CYCLES || spins > WAIT_MAX_SPINS) {
+        atomicExch(err, code);
+        __threadfence_system();
+        __trap();
+      }
     }
   }
 }
@@ -157,6 +176,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

@@ -218,7 +218,19 @@ def fit_full():
             warnings.simplefilter("ignore")
             gp.fit(X, y)
             yhat, mse = gp.predict(Xc, eval_MSE=True)
+        # the optimiser is chaotic in the last bits (it is fed an inconsistent gradient) and draws its
+        # restarts / sigma2 start from the global RNG: record the spread of the reference's OWN result over seeds
+        llf_seeds = []
+        for seed in range(12):
+            g2 = make_gp(corr, D, mode, True, 1e-2)
+            g2.thetaL, g2.thetaU, g2.theta0, g2.random_start = np.full(D, 1e-2), np.full(D, 1e2), np.full(D, 1.0), 2
+            np.random.seed(seed)
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                g2.fit(X, y)
+            llf_seeds.append(float(g2.log_likelihood_))
         cases[name] = dict(X=X, y=y, Xc=Xc, corr=corr, mode=mode, theta=gp.theta_, llf=gp.log_likelihood_,
+                           llf_seeds=np.array(llf_seeds),
                            sigma2=np.atleast_1d(gp.sigma2)[0], noise_var=np.atleast_1d(gp.noise_var)[0],
                            eval_count=gp.eval_count, yhat=yhat.ravel(), mse=mse.ravel(),
                            beta=np.asarray(gp.mean.beta).ravel())

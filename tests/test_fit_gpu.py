@@ -53,43 +53,65 @@ def test_matern52_gradient_is_the_true_derivative():
         assert g[i] == pytest.approx(fd, rel=2e-4, abs=1e-6), i
 
 
-@pytest.mark.parametrize("name", sorted(FITS))
-def test_full_fit_reaches_reference_optimum(name):
-    """fit() = host L-BFGS-B restarts (global numpy RNG) on the device likelihood + gradient.  The optimiser
-    path is chaotic in the last bits, so parity is on the outcome: final likelihood and predictions."""
-    c = FITS[name]
+def _fit_kwargs(c):
     D = c["X"].shape[1]
     mode = int(c["mode"])
-    kw = dict(mean=b2.constant_trend(D), corr=CORR_ARG[int(c["corr"])], thetaL=[1e-2] * D, thetaU=[1e2] * D,
-              theta0=[1.0] * D, random_start=2)
+    kw = dict(corr=CORR_ARG[int(c["corr"])], thetaL=[1e-2] * D, thetaU=[1e2] * D, theta0=[1.0] * D, random_start=2)
     if mode == go.MODE_NOISELESS:
         kw.update(nugget=None)
     elif mode == go.MODE_NOISY:
         kw.update(nugget=1e-2)
     else:
         kw.update(nugget=1e-2, noise_estim=True)
-    gp = b2.GaussianProcess(**kw)
+    return D, mode, kw
+
+
+@pytest.mark.parametrize("name", sorted(FITS))
+def test_full_fit_matches_reference_over_seeds(name):
+    """fit() = host L-BFGS-B restarts (global numpy RNG) on the device likelihood + gradient (gpr.py:1058-1197).
+    The reference feeds L-BFGS-B an inconsistent gradient (quirk g4) and draws sigma2 / restarts from the global
+    RNG, so its OWN result varies wildly with the seed (golden ``llf_seeds``: e.g. -28 / -152 / -6863 for one
+    data set) and last-bit differences of the objective change the path.  Parity is therefore on the outcome over
+    the same 12 seeds: the best optimum is the reference's best, and the typical (median) run is as good."""
+    c = FITS[name]
+    D, mode, kw = _fit_kwargs(c)
+    ref = np.asarray(c["llf_seeds"], dtype=float)
+    ours = []
+    for seed in range(len(ref)):
+        gp = b2.GaussianProcess(mean=b2.constant_trend(D), **kw)
+        np.random.seed(seed)
+        assert gp.fit(c["X"], c["y"]) is gp and gp.is_fitted
+        assert np.isfinite(gp.log_likelihood_)
+        ours.append(gp.log_likelihood_)
+    ours = np.array(ours)
+    assert ours.max() >= ref.max() - 1e-5 * abs(ref.max()), (ours, ref)
+    assert np.median(ours) >= np.median(ref) - 1e-3 * abs(np.median(ref)), (ours, ref)
+
+
+@pytest.mark.parametrize("name", sorted(FITS))
+def test_full_fit_state_is_consistent(name):
+    c = FITS[name]
+    D, mode, kw = _fit_kwargs(c)
+    gp = b2.GaussianProcess(mean=b2.constant_trend(D), **kw)
     np.random.seed(5)
-    assert gp.fit(c["X"], c["y"]) is gp and gp.is_fitted
-    ref_llf = float(c["llf"])
-    # L-BFGS-B is fed the reference's inconsistent gradient (quirk g4) and amplifies last-bit differences of
-    # the objective, so the two runs may end in different local optima: ours must be at least as good
-    assert gp.log_likelihood_ >= ref_llf - 1e-4 * abs(ref_llf)
+    gp.fit(c["X"], c["y"])
     yh, ms = gp.predict(c["Xc"], eval_MSE=True)
-    if abs(gp.log_likelihood_ - ref_llf) <= 1e-6 * abs(ref_llf):      # same optimum: predictions agree too
+    if abs(gp.log_likelihood_ - float(c["llf"])) <= 1e-6 * abs(float(c["llf"])):   # same optimum as the reference's seed-5 run
         np.testing.assert_allclose(yh.ravel(), c["yhat"], rtol=0, atol=2e-2 * np.abs(c["yhat"]).max())
-    # and the state is self-consistent with a fixed-theta fit at the found optimum
+    # the fitted state is the fixed-theta fit at the optimum found (a fresh trend object: fit() stored beta in gp's)
     last = None if mode == go.MODE_NOISELESS else gp._par_last
-    # (a fresh trend object: fit() stored the estimated beta in the shared one, which would turn gp2 into simple kriging)
-    gp2 = b2.GaussianProcess(**dict(kw, mean=b2.constant_trend(D)))
+    gp2 = b2.GaussianProcess(mean=b2.constant_trend(D), **kw)
     assert gp2.fit_fixed(c["X"], c["y"], gp.theta_, last) == gp.log_likelihood_
     y2, m2 = gp2.predict(c["Xc"], eval_MSE=True)
     np.testing.assert_array_equal(y2, yh)
     np.testing.assert_array_equal(m2, ms)
-    # warm start: a second fit starts from theta_ (gpr.py:1095-1096) and may not get worse
+    # warm start from theta_ (gpr.py:1095-1096); only theta is warm-started, sigma2 / alpha are redrawn (:1101-1107),
+    # so "not worse" holds where theta is the whole parameter vector
     l1 = gp.log_likelihood_
     gp.fit(c["X"], c["y"])
-    assert gp.log_likelihood_ >= l1 - 1e-6 * abs(l1)
+    assert gp.is_fitted and np.isfinite(gp.log_likelihood_)
+    if mode == go.MODE_NOISELESS:
+        assert gp.log_likelihood_ >= l1 - 1e-6 * abs(l1)
 
 
 def test_isotropic_theta_gradient_quirk():
