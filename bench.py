@@ -119,6 +119,16 @@ def cpu_step(ora, go, w, params, Xc):
     return best
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm is meant to use every host core"""
+    try:
+        from threadpoolctl import threadpool_limits
+
+        threadpool_limits(limits=os.cpu_count() or 1)
+    except Exception:
+        pass
+
+
 def threads_used():
     try:
         from threadpoolctl import threadpool_info
@@ -134,6 +144,7 @@ def run_reference(args, w, params):
         return
     from bayesian_optimization_b200 import workloads as wl
 
+    use_all_host_threads()
     sample = args.cpu_sample or 4 * cpu_chunk(w.N, w.D)
     ora, go = cpu_fit(w)
     Xc = wl.canonical_candidates(sample, w.D)
@@ -176,6 +187,8 @@ def run_b200(args, w, params):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL prints its version banner there)
         dist.init_process_group("nccl", device_id=dev)
     M = args.m_per_gpu or w.M_per_gpu
     offset = rank * M
@@ -184,7 +197,7 @@ def run_b200(args, w, params):
     # ---- fit once (replicated per rank, deterministic) -------------------------------------------
     X, y, theta = wl.canonical_problem(w.N, w.D)
     gp = b2.GaussianProcess(mean=b2.constant_trend(w.D), corr=w.corr, thetaL=[1e-5] * w.D, thetaU=[1e2] * w.D,
-                            nugget=w.nugget)
+                            nugget=w.nugget, device=local)  # one engine per rank, on this rank's GPU
     t0 = time.perf_counter()
     llf = gp.fit_fixed(X, y, theta, 1.0)
     fit_wall_ms = 1e3 * (time.perf_counter() - t0)
@@ -323,6 +336,7 @@ def run_b200(args, w, params):
         "roofline": roofline,
     }
     if world == 1 and not args.no_cpu_baseline:
+        use_all_host_threads()
         sample = args.cpu_sample or 16 * cpu_chunk(w.N, w.D)
         ora, go = cpu_fit(w)
         Xc = wl.canonical_candidates(sample, w.D)
