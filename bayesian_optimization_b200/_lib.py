@@ -20,7 +20,7 @@ ACQ_EI, ACQ_PI, ACQ_UCB, ACQ_MGFI = range(4)
 HOST, DEVICE = 0, 1
 PREC_FP64, PREC_FAST = 0, 1
 STATE_L, STATE_LINV, STATE_GAMMA, STATE_YT, STATE_FT, STATE_RHO, STATE_BETA, STATE_G, STATE_R = range(9)
-N_TIMINGS = 8
+N_TIMINGS = 12
 
 E_ARG, E_CUDA, E_STATE, E_NODEVICE = -1, -2, -3, -4
 
@@ -45,6 +45,7 @@ SIGNATURES = {
     "b200bo_set_precision": (C.c_int, [C.c_void_p, C.c_int]),
     "b200bo_set_keep_R": (C.c_int, [C.c_void_p, C.c_int]),
     "b200bo_set_fast_kernel": (C.c_int, [C.c_void_p, C.c_int]),
+    "b200bo_set_fast_products": (C.c_int, [C.c_void_p, C.c_int]),
     "b200bo_set_train": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "b200bo_factor": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double,
                                 C.c_int, C.c_void_p, _dp, _dp, _dp, _ip]),
@@ -136,6 +137,9 @@ class Engine:
 
     def set_fast_kernel(self, generation: int):
         _check(self._lib.b200bo_set_fast_kernel(self._h, int(generation)))
+
+    def set_fast_products(self, products: int):
+        _check(self._lib.b200bo_set_fast_products(self._h, int(products)))
 
     def set_keep_R(self, keep: bool):
         _check(self._lib.b200bo_set_keep_R(self._h, int(bool(keep))))

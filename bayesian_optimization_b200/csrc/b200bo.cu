@@ -110,9 +110,12 @@ struct b200bo_ctx {
   DevBuf<double> Xc, Kst, yhat, sumsq, dotf, mse, params, part_val, best_val, vals;
   DevBuf<long long> part_idx, best_idx;
   // tensor-core (B200BO_PREC_FAST) state, built lazily after factor()
-  bool fast_ready = false, calibrated = false;
+  bool fast_ready = false;
+  bool calibrated[2] = {false, false};  // [0]: one-product first pass, [1]: three-product pass
   int DP = 0, b_scale_log2 = 0;
-  double dy_cal = 0, ds_cal = 0;
+  double dy_cal[2] = {0, 0}, ds_cal[2] = {0, 0};
+  int fast_products = 1;   // products of the first pass (1: fp16 operands; 3: split fp16); set_fast_products
+  bool escalate = false;   // the one-product band was too wide for this fit: go straight to three products
   DevBuf<__half> Lh, Ll;
   DevBuf<float> Xs, dbg_w;
   DevBuf<double> rs_part, cscale, fvec, f_yhat, f_sumsq, f_dotf, stage[2], Xband, errout, band_hiB;
@@ -274,7 +277,15 @@ int b200bo_set_fast_kernel(b200bo_handle h, int generation) {
   CHECK_ARG(generation == 1 || generation == 2, "generation is 1 or 2");
   h->fast_kernel_pref = generation;
   h->fast_ready = false;
-  h->calibrated = false;
+  h->calibrated[0] = h->calibrated[1] = false;
+  return 0;
+}
+
+int b200bo_set_fast_products(b200bo_handle h, int products) {
+  CHECK_ARG(h, "handle is NULL");
+  CHECK_ARG(products == 1 || products == 3, "products is 1 or 3");
+  h->fast_products = products;
+  h->escalate = false;
   return 0;
 }
 
@@ -331,7 +342,8 @@ int b200bo_factor(b200bo_handle h, int corr, const double* theta, int n_theta, i
   const size_t nn = (size_t)ld * ld;
   h->factored = false;
   h->fast_ready = false;
-  h->calibrated = false;
+  h->calibrated[0] = h->calibrated[1] = false;
+  h->escalate = false;
   CU_TRY(h->A.reserve(nn));
   CU_TRY(h->W.reserve(nn));
   CU_TRY(h->S.reserve(nn));
@@ -607,7 +619,7 @@ int b200bo_get_state(b200bo_handle h, int what, double* out, size_t n_elems) {
 struct LaunchCount {
   int all = 0, contract = 0;
 };
-static const int RS_SMALL_MAX = 4096;  // candidates up to which the row-parallel contraction is used
+static const int RS_SMALL_MAX = 1024;  // candidates up to which the row-parallel contraction is used
 
 static int fp64_moments(b200bo_handle h, const double* xc_dev, int m, double* yh, int eval_mse, PhaseTimer* pt,
                         LaunchCount* lc) {
@@ -877,12 +889,12 @@ static int ensure_fast_state(b200bo_handle h) {
   }
   CU_TRY(cudaStreamSynchronize(st));
   h->fast_ready = true;
-  h->calibrated = false;
+  h->calibrated[0] = h->calibrated[1] = false;
   return 0;
 }
 
 // one launch of the fused tensor-core kernel over m device-resident candidates; outputs at out_off
-static int launch_fused(b200bo_handle h, const double* xc_dev, long long m, size_t out_off) {
+static int launch_fused(b200bo_handle h, const double* xc_dev, long long m, size_t out_off, int nprod = 3) {
   if (h->use_v2) {
     fk2::Fused2Args a;
     a.Xc = xc_dev; a.cscale = h->cscale.p; a.cmean = h->cmean.p; a.aux = h->aux2.p;
@@ -896,7 +908,7 @@ static int launch_fused(b200bo_handle h, const double* xc_dev, long long m, size
     const int grid = (int)std::min<long long>(h->num_sms, tiles);
 #define FK2_LAUNCH(C)                                                                                               \
   do {                                                                                                             \
-    auto kern = fk2::predict_fused_tc2_kernel<C>;                                                                  \
+    auto kern = nprod == 1 ? fk2::predict_fused_tc2_kernel<C, 1> : fk2::predict_fused_tc2_kernel<C, 3>;             \
     CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fk2::SMEM_BYTES));              \
     kern<<<grid, fk2::NT2, fk2::SMEM_BYTES, h->stream>>>(h->map2_hi, h->map2_lo, h->map2_xh, h->map2_xl, a);        \
   } while (0)
@@ -961,6 +973,7 @@ static int fast_errors(b200bo_handle h, const long long* list_dev, long long idx
 }
 
 static const int FAST_CHUNK_TILES = 8;        // candidate tiles per SM per fused launch when streaming from the host
+static const int RESCORE_DIRECT_MAX = 2048;   // widest one-product band that goes straight to the fp64 re-score
 
 static int run_candidates_fast(b200bo_handle h, const double* Xc, int64_t M, int loc, int eval_mse, double* yhat_out,
                                double* mse_out, int acq_id, int minimize, double plugin, const double* params, int q,
@@ -970,6 +983,10 @@ static int run_candidates_fast(b200bo_handle h, const double* Xc, int64_t M, int
   const bool dev = loc == B200BO_DEVICE;
   int rc;
   if ((rc = ensure_fast_state(h))) return rc;
+  // first pass: one fp16 product when only the arg-max is wanted (its band is re-scored exactly anyway); three
+  // products for predict() (documented ~1e-6 moments) or once a fit's one-product band proved too wide
+  const int nprod = (do_acq && h->use_v2 && h->fast_products == 1 && !h->escalate) ? 1 : 3;
+  const int ci = nprod == 1 ? 0 : 1;
   if ((rc = ensure_predict_ws(h, q, false))) return rc;
   cudaStream_t st = h->stream;
   const int D = h->D, Mc = h->Mc;
@@ -990,7 +1007,7 @@ static int run_candidates_fast(b200bo_handle h, const double* Xc, int64_t M, int
   // ---- phase I: the fused tensor-core pass over all candidates ---------------------------------------
   pt.begin(1);
   if (dev) {
-    if ((rc = launch_fused(h, Xc, M, 0))) return rc;
+    if ((rc = launch_fused(h, Xc, M, 0, nprod))) return rc;
     ++fused_launches;
   } else {
     // stream the host candidates through two staging buffers; copies run on their own stream
@@ -1009,7 +1026,7 @@ static int run_candidates_fast(b200bo_handle h, const double* Xc, int64_t M, int
       CU_TRY(cudaMemcpyAsync(h->stage[b].p, Xc + (size_t)a * D, (size_t)m * D * 8, cudaMemcpyHostToDevice, h->copy_stream));
       CU_TRY(cudaEventRecord(h->ev_copied[b], h->copy_stream));
       CU_TRY(cudaStreamWaitEvent(st, h->ev_copied[b], 0));
-      if ((rc = launch_fused(h, h->stage[b].p, m, (size_t)a))) return rc;
+      if ((rc = launch_fused(h, h->stage[b].p, m, (size_t)a, nprod))) return rc;
       CU_TRY(cudaEventRecord(h->ev_used[b], st));
       ++fused_launches;
     }
@@ -1053,7 +1070,7 @@ static int run_candidates_fast(b200bo_handle h, const double* Xc, int64_t M, int
     CU_TRY(cudaStreamSynchronize(st));
     return 0;
   };
-  if (!h->calibrated) {
+  if (!h->calibrated[ci]) {
     const int n = (int)std::min<int64_t>(M, std::min(Mc, 2048));
     const double* xc = Xc;
     if (!dev) {
@@ -1063,9 +1080,9 @@ static int run_candidates_fast(b200bo_handle h, const double* Xc, int64_t M, int
     if ((rc = fp64_moments(h, xc, n, h->yhat.p, 1, nullptr, &lc))) return rc;
     double ey, es;
     if ((rc = fast_errors(h, nullptr, 0, n, &ey, &es))) return rc;
-    h->dy_cal = 8.0 * ey + 1e-13;
-    h->ds_cal = 8.0 * es + 1e-13 * h->sigma2;
-    h->calibrated = true;
+    h->dy_cal[ci] = 8.0 * ey + 1e-13;
+    h->ds_cal[ci] = 8.0 * es + 1e-13 * h->sigma2;
+    h->calibrated[ci] = true;
   }
 
   // ---- phase II / III: band selection, exact re-score; widen and repeat if the band shows larger errors --
@@ -1078,7 +1095,7 @@ static int run_candidates_fast(b200bo_handle h, const double* Xc, int64_t M, int
   CU_TRY(h->band_hiB.reserve((size_t)LIST0_CAP * q));
   CU_TRY(h->Xband.reserve((size_t)Mc * D));
   int rescored = 0, passes = 0;
-  double dy = h->dy_cal, ds = h->ds_cal;
+  double dy = h->dy_cal[ci], ds = h->ds_cal[ci];
   std::vector<long long> list;
   for (;;) {
     ++passes;
@@ -1107,6 +1124,12 @@ static int run_candidates_fast(b200bo_handle h, const double* Xc, int64_t M, int
     CU_TRY(cudaMemcpyAsync(counts, h->band_count.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
     const int count = counts[1];
+    if (nprod == 1 && (counts[0] > LIST0_CAP || count > RESCORE_DIRECT_MAX || passes > 2)) {
+      // the one-product pass cannot separate the top of this criterion: three products for the rest of this fit
+      h->escalate = true;
+      return run_candidates_fast(h, Xc, M, loc, eval_mse, yhat_out, mse_out, acq_id, minimize, plugin, params, q,
+                                 best_val, best_idx, fell_back);
+    }
     if (counts[0] > LIST0_CAP || passes > 4) {  // degenerate (flat criterion) or unstable error estimate
       *fell_back = true;
       return 0;
@@ -1138,8 +1161,8 @@ static int run_candidates_fast(b200bo_handle h, const double* Xc, int64_t M, int
     if (ey_max <= 0.5 * dy && es_max <= 0.5 * ds) break;  // the band was wide enough for the errors it shows
     dy = std::max(dy, 4.0 * ey_max);
     ds = std::max(ds, 4.0 * es_max);
-    h->dy_cal = std::max(h->dy_cal, dy);
-    h->ds_cal = std::max(h->ds_cal, ds);
+    h->dy_cal[ci] = std::max(h->dy_cal[ci], dy);
+    h->ds_cal[ci] = std::max(h->ds_cal[ci], ds);
   }
   pt.end(2);
   CU_TRY(cudaEventRecord(e1, st));
@@ -1149,6 +1172,7 @@ static int run_candidates_fast(b200bo_handle h, const double* Xc, int64_t M, int
   cudaEventElapsedTime(&ms, e0, e1);
   h->timings[0] = ms; h->timings[1] = 0; h->timings[2] = pt.total(1); h->timings[3] = pt.total(2);
   h->timings[4] = fused_launches; h->timings[5] = lc.all; h->timings[6] = rescored; h->timings[7] = passes;
+  h->timings[8] = nprod; h->timings[9] = (nprod == 3 && h->escalate) ? 1 : 0;
   return 0;
 }
 

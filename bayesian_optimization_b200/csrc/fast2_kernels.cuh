@@ -103,7 +103,9 @@ __device__ __forceinline__ float corr_from_acc(float acc) {
   return fmaf(acc, 1.0f / 3.0f, 1.0f + t) * e;  // MATERN52
 }
 
-template <int CORR>
+// NPROD = 3: hi*hi + hi*lo + lo*hi (~2^-22);  NPROD = 1: hi*hi only (fp16 operands, ~2^-11) -- the cheap first pass
+// whose arg-max band is then re-scored exactly
+template <int CORR, int NPROD>
 __global__ void __launch_bounds__(NT2, 1)
 predict_fused_tc2_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
                          const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
@@ -169,9 +171,9 @@ predict_fused_tc2_kernel(const __grid_constant__ CUtensorMap map_hi, const __gri
               if (n0 >= ld || k0 >= n0 + NB) continue;  // beyond the matrix / above the diagonal
               const uint32_t b = it % B_SLOTS, ph = (it / B_SLOTS) & 1;
               mbar_wait(BAR(BAR_EMPTY_B + b), ph ^ 1, p.err, 1);
-              mbar_arrive_expect_tx(BAR(BAR_FULL_B + b), B_SLOT_BYTES);
+              mbar_arrive_expect_tx(BAR(BAR_FULL_B + b), NPROD == 3 ? B_SLOT_BYTES : B_PLANE);
               tma_load_2d(sbase + OFF_B + b * B_SLOT_BYTES, &map_hi, k0, n0, BAR(BAR_FULL_B + b));
-              tma_load_2d(sbase + OFF_B + b * B_SLOT_BYTES + B_PLANE, &map_lo, k0, n0, BAR(BAR_FULL_B + b));
+              if (NPROD == 3) tma_load_2d(sbase + OFF_B + b * B_SLOT_BYTES + B_PLANE, &map_lo, k0, n0, BAR(BAR_FULL_B + b));
               ++it;
             }
         }
@@ -250,8 +252,10 @@ predict_fused_tc2_kernel(const __grid_constant__ CUtensorMap map_hi, const __gri
               for (int ks = 0; ks < KC / 16; ++ks) {
                 const uint64_t o = (uint64_t)(ks * 2);
                 umma_f16(td, da_hi + o, db_hi + o, idesc_main, (k0 | ks) != 0);
-                umma_f16(td, da_hi + o, db_lo + o, idesc_main, 1);
-                umma_f16(td, da_lo + o, db_hi + o, idesc_main, 1);
+                if (NPROD == 3) {
+                  umma_f16(td, da_hi + o, db_lo + o, idesc_main, 1);
+                  umma_f16(td, da_lo + o, db_hi + o, idesc_main, 1);
+                }
               }
               umma_commit(BAR(BAR_EMPTY_B + b));
               ++ib;
@@ -395,14 +399,16 @@ predict_fused_tc2_kernel(const __grid_constant__ CUtensorMap map_hi, const __gri
             for (int i = 0; i < 4; ++i) {
               const float v0 = kv[8 * c + 2 * i], v1 = kv[8 * c + 2 * i + 1];
               const __half2 h = __floats2half2_rn(v0, v1);
-              const float2 hf = __half22float2(h);
-              const __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
               hi[i] = *(const uint32_t*)&h;
-              lo[i] = *(const uint32_t*)&l;
+              if (NPROD == 3) {
+                const float2 hf = __half22float2(h);
+                const __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+                lo[i] = *(const uint32_t*)&l;
+              }
             }
             const uint32_t off = row_off + (uint32_t)((((kq * 2 + c) ^ (m & 7)) & 7) * 16);
             *(uint4*)(a_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            *(uint4*)(a_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            if (NPROD == 3) *(uint4*)(a_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           }
           tc_fence_before();    // our tcgen05.ld of the Gram block is ordered before the MMA that reuses it
           fence_proxy_async();  // generic-proxy stores -> visible to the tensor core

@@ -12,7 +12,7 @@
 namespace b2 {
 
 constexpr int NB = 64;  // Cholesky / TRTRI block size
-constexpr size_t CHOL_DIAG_SMEM = 2 * NB * (NB + 1) * sizeof(double);
+constexpr size_t CHOL_DIAG_SMEM = (2 * NB * (NB + 1) + 32 * 33 + 3 * NB) * sizeof(double);
 
 // ---------------------------------------------------------------------------------------------------
 // Kernel-matrix assembly.  One CTA = one 64x64 tile (ti >= tj) of the lower triangle, mirrored into the
@@ -111,46 +111,111 @@ __global__ void __launch_bounds__(256) kmat_assemble_kernel(AssembleArgs p) {
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) chol_diag_kernel(double* __restrict__ A, int ld, double* __restrict__ Dinv,
                                                         int* __restrict__ status) {
+  // 64 x 64 diagonal block: factor + inverse, one CTA.  The sequential part is kept to ONE barrier and one
+  // reciprocal per column: the trailing update uses the unscaled column and 1/d_j, the 1/sqrt(d_j) scaling of
+  // all columns is applied once at the end, and the inverse is built by block recursion 16 -> 32 -> 64.
   extern __shared__ __align__(16) double sm_cd[];
   double(*s)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(sm_cd);
   double(*x)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(sm_cd + NB * (NB + 1));  // inverse, x[r][c]
+  double(*t)[33] = reinterpret_cast<double(*)[33]>(sm_cd + 2 * NB * (NB + 1));     // 32 x 32 scratch
+  double* rs = sm_cd + 2 * NB * (NB + 1) + 32 * 33;                                // 1 / sqrt(d_c) = 1 / L_cc
   const int tid = threadIdx.x;
-  for (int e = tid; e < NB * NB; e += 256) {
-    int r = e / NB, c = e % NB;
-    s[r][c] = A[(size_t)r * ld + c];
+  double* colbuf = rs + NB;  // [2][NB] column j of the running factorisation, double-buffered
+  // thread (tr, tc) keeps the 16 elements (tr + 16 i, tc + 16 k) in registers for the whole factorisation
+  const int tr = tid >> 4, tc = tid & 15;
+  double a[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) a[i][k] = A[(size_t)(tr + 16 * i) * ld + tc + 16 * k];
+  for (int e = tid; e < NB * NB; e += 256) x[e / NB][e % NB] = 0.0;
+  // ---- right-looking factorisation on unscaled columns: a[r][c] -= a[r][j] a[c][j] / d_j  (r >= c > j) ----
+#pragma unroll
+  for (int kj = 0; kj < 4; ++kj) {  // unrolled so that a[][] is indexed statically (stays in registers)
+#pragma unroll 1
+    for (int jj = 0; jj < 16; ++jj) {
+      const int j = 16 * kj + jj;
+      double* cb = colbuf + (j & 1) * NB;
+      if (tc == jj) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) cb[tr + 16 * i] = a[i][kj];
+      }
+      __syncthreads();
+      const double dinv = __drcp_rn(cb[j]);
+      double li[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) li[i] = cb[tr + 16 * i] * dinv;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (k < kj) continue;  // columns of earlier groups are final
+        const int c = tc + 16 * k;
+        if (c > j) {
+          const double lc = cb[c];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (tr + 16 * i >= c) a[i][k] = fma(-li[i], lc, a[i][k]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s[tr + 16 * i][tc + 16 * k] = a[i][k];
+  __syncthreads();
+  if (tid < NB) {
+    const double d = s[tid][tid];
+    // scipy's cholesky raises LinAlgError on a pivot <= 0 -> llf = -inf (gpr.py:946).  R has a unit diagonal in
+    // every estimation mode, so a pivot below 16 eps has lost all its digits: exactly singular matrices (duplicate
+    // points without nugget), whose computed pivot is +-O(eps) by rounding luck, are rejected deterministically.
+    if (!(d > 16.0 * 2.220446049250313e-16)) atomicOr(status, 1);
+    rs[tid] = 1.0 / sqrt(d);
   }
   __syncthreads();
-  for (int j = 0; j < NB; ++j) {
-    if (tid == 0) {
-      double d = s[j][j];
-      if (!(d > 0.0)) atomicOr(status, 1);
-      s[j][j] = sqrt(d);
-    }
-    __syncthreads();
-    const double djj = s[j][j];
-    if (tid > j && tid < NB) s[tid][j] /= djj;
-    __syncthreads();
-    for (int e = tid; e < NB * NB; e += 256) {
-      int r = e / NB, c = e % NB;
-      if (c > j && r >= c) s[r][c] -= s[r][j] * s[c][j];
-    }
-    __syncthreads();
+  for (int e = tid; e < NB * NB; e += 256) {
+    const int r = e / NB, c = e % NB;
+    if (r > c) s[r][c] *= rs[c];
+    else if (r == c) s[r][c] = s[r][c] * rs[c];  // d / sqrt(d)
+    else s[r][c] = 0.0;
   }
-  // inverse by forward substitution, one column per thread: L x_c = e_c
+  __syncthreads();
+  // ---- inverse: four 16 x 16 diagonal blocks by forward substitution (one thread per column) ----
   if (tid < NB) {
-    const int c = tid;
-    for (int r = 0; r < c; ++r) x[r][c] = 0.0;
-    x[c][c] = 1.0 / s[c][c];
-    for (int r = c + 1; r < NB; ++r) {
+    const int c = tid, b0 = c & ~15;
+    x[c][c] = rs[c];
+    for (int r = c + 1; r < b0 + 16; ++r) {
       double acc = 0.0;
       for (int k = c; k < r; ++k) acc += s[r][k] * x[k][c];
-      x[r][c] = -acc / s[r][r];
+      x[r][c] = -acc * rs[r];
     }
   }
   __syncthreads();
+  // ---- merges: [[A,0],[B,C]]^-1 = [[A^-1,0],[-C^-1 B A^-1, C^-1]] for half = 16, then 32 ----
+  for (int half = 16; half < NB; half *= 2) {
+    const int nblk = NB / (2 * half);  // independent merges at this level
+    const int per = half * half;
+    // T = B A^-1   (A^-1 lower: k >= col)
+    for (int e = tid; e < nblk * per; e += 256) {
+      const int q = e / per, i = (e % per) / half, jj = e % half;
+      const int o = q * 2 * half;
+      double acc = 0.0;
+      for (int k = jj; k < half; ++k) acc += s[o + half + i][o + k] * x[o + k][o + jj];
+      t[q * half + i][jj] = acc;  // (nblk * half) x half <= 32 x 32
+    }
+    __syncthreads();
+    // X_B = -C^-1 T   (C^-1 lower: k <= row)
+    for (int e = tid; e < nblk * per; e += 256) {
+      const int q = e / per, i = (e % per) / half, jj = e % half;
+      const int o = q * 2 * half;
+      double acc = 0.0;
+      for (int k = 0; k <= i; ++k) acc += x[o + half + i][o + half + k] * t[q * half + k][jj];
+      x[o + half + i][o + jj] = -acc;
+    }
+    __syncthreads();
+  }
   for (int e = tid; e < NB * NB; e += 256) {
     int r = e / NB, c = e % NB;
-    A[(size_t)r * ld + c] = c <= r ? s[r][c] : 0.0;
+    A[(size_t)r * ld + c] = s[r][c];
     Dinv[e] = x[r][c];
   }
 }

@@ -235,7 +235,7 @@ def run_b200(args, w, params):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        kern = np.zeros(8)
+        kern = np.zeros(b2._lib.N_TIMINGS)
         out = None
         for _ in range(steps):
             out = fn()
@@ -301,12 +301,19 @@ def run_b200(args, w, params):
                     mac += NB_ * min(kext, -(-(n0 + NB_) // 64) * 64)
             if gen2:
                 mac += (kext // 64) * 64 * 16 * (-(-w.D // 16))
-        exe = cand_per_launch * 3 * 2.0 * mac / (launch_ms * 1e-3) / 1e12
+        nprod = int(round(kern[8] / args.steps))
+        if gen2:  # the Gram MMAs always take three products
+            gram = sum((min(ld, WC_ * (s_ + 1)) // 64) * 64 * 16 * (-(-w.D // 16)) for s_ in range(-(-ld // WC_)))
+            mac_exec = nprod * (mac - gram) + 3 * gram
+        else:
+            mac_exec = 3 * mac
+        exe = cand_per_launch * 2.0 * mac_exec / (launch_ms * 1e-3) / 1e12
         roofline.update({
             "kernel": ("predict_fused_tc2_kernel" if gen2 else "predict_fused_tc_kernel") + " (tcgen05.mma kind::f16, 3 split-fp16 products per MAC, fp32 TMEM accumulators)",
             "executed_tensor_tflops": exe, "executed_frac": exe / peak,
-            "note": "achieved counts ALGORITHMIC flops (N^2 per candidate); the split scheme executes ~3.4x that on the "
-                    "tensor pipe, so frac <= ~0.3 by construction; executed_frac is the tensor-pipe utilisation",
+            "products_per_mac": nprod,
+            "note": "achieved counts ALGORITHMIC flops (N^2 per candidate); the tensor pipe executes products_per_mac x that "
+                    "(+ diagonal blocks and the Gram MMAs); executed_frac is the tensor-pipe utilisation",
         })
     else:
         roofline.update({
@@ -316,11 +323,12 @@ def run_b200(args, w, params):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f16x2-split/f32-acc + f64 re-score" if fast else "f64", "data": "synthetic",
+        "dtype": "f16/f32-acc + f64 re-score" if fast else "f64", "data": "synthetic",
         "config": {"workload": w.name, "describe": w.describe, "N": w.N, "D": w.D, "corr": w.corr, "acq": w.acq,
                    "q": w.q, "candidates_per_gpu_per_step": M, "candidates_per_step": world * M,
                    "parallelism": f"candidate-shards x{world}",
-                   "precision": ("tcgen05 split-fp16 (3 products) + exact fp64 re-score of the arg-max band" if fast
+                   "precision": (f"tcgen05 fp16 first pass ({int(round(kern[8] / args.steps))} product(s) per MAC, fp32 TMEM "
+                                 "accumulators) + exact fp64 re-score of the arg-max band" if fast
                                  else "fp64 DMMA parity path"),
                    "rescored_per_step": kern[6] / args.steps, "band_passes_per_step": kern[7] / args.steps,
                    "l2": "inputs_exceed_l2 (candidates + k* workspace > 126 MB per step)",

@@ -94,6 +94,10 @@ int b200bo_set_keep_R(b200bo_handle h, int keep);
 /* which tensor-core kernel B200BO_PREC_FAST uses: 2 (default) = Gram product on the tensor cores where the kernel
  * is a function of the L2 distance, else generation 1; 1 = always the first-generation kernel (A/B comparisons) */
 int b200bo_set_fast_kernel(b200bo_handle h, int generation);
+/* fp16 products per MAC of the first tensor-core pass of b200bo_acq: 1 (default; operands rounded to fp16, ~1e-3 on
+ * the variance -- the band it leaves is re-scored in fp64, or the call escalates to 3 when the band is too wide) or
+ * 3 (split fp16, ~1e-6).  b200bo_predict always uses 3. */
+int b200bo_set_fast_products(b200bo_handle h, int products);
 
 /* -- training data: GaussianProcess._check_data (gpr.py:279-310) --------------------------------------
  * X (N,D), y (N,) float64 host pointers.  The pairwise-distance pre-pass l1_cross_distances(X)
@@ -152,8 +156,9 @@ int b200bo_debug_fast_rt(b200bo_handle h, const double* Xc, int64_t M, float* ou
  *   [0] whole call on device  [1] k* build kernels  [2] L^-1 k* contraction kernels (the dominant kernel)
  *   [3] acquisition + arg-max kernels  [4] number of contraction launches  [5] number of all launches
  *   [6] fp64 re-scored candidates (FAST only)  [7] band passes (FAST only)
- * FAST: [1] = 0 (the k* build is fused), [2] = fused tensor-core kernel, [3] = band selection + exact re-score */
-#define B200BO_N_TIMINGS 8
+ * FAST: [1] = 0 (the k* build is fused), [2] = fused tensor-core kernel, [3] = band selection + exact re-score,
+ *       [8] fp16 products per MAC of the pass that produced the result (1 or 3)  [9] 1 if this call escalated 1 -> 3 */
+#define B200BO_N_TIMINGS 12
 int b200bo_get_timings(b200bo_handle h, double* out, int n);
 /* timings (ms) of the last factor(): [0] total [1] assembly [2] cholesky [3] trtri [4] solves  [5] launches */
 int b200bo_get_fit_timings(b200bo_handle h, double* out, int n);

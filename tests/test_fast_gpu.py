@@ -76,9 +76,13 @@ def test_fast_predict_tolerance(N, D, corr, corr_id):
     (_lib.ACQ_UCB, [0.1, 0.5, 2.0]),
     (_lib.ACQ_PI, [1e-10, 0.05]),
 ])
+@pytest.mark.parametrize("products", [1, 3])
 @pytest.mark.parametrize("N,D,corr,corr_id", CASES[:3])
-def test_fast_argmax_is_exact(N, D, corr, corr_id, acq, params):
+def test_fast_argmax_is_exact(N, D, corr, corr_id, acq, params, products):
+    """products = 1: fp16 operands in the first pass (~1e-3 on the variance), band re-scored in fp64, escalation to
+    three products when the band is too wide; products = 3: split fp16 (~1e-6).  Same exactness bar for both."""
     gp, ora = make(N, D, corr, corr_id)
+    gp.engine.set_fast_products(products)
     M = 60000
     Xc = workloads.canonical_candidates(M, D)
     yo, mo = go.predict_chunked(ora, Xc, 1024)
