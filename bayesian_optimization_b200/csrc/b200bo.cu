@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -119,7 +120,7 @@ struct b200bo_ctx {
   DevBuf<__half> Lh, Ll;
   DevBuf<float> Xs, dbg_w;
   DevBuf<double> rs_part, cscale, fvec, f_yhat, f_sumsq, f_dotf, stage[2], Xband, errout, band_hiB;
-  DevBuf<long long> band_list, band_list0, thr_key;
+  DevBuf<long long> band_list, band_list0, thr_key, trace;
   DevBuf<int> band_count, err_flag;
   CUtensorMap map_hi, map_lo;
   // second-generation kernel (Gram product on the tensor cores): its own operand copies
@@ -223,6 +224,12 @@ int b200bo_create(int device, b200bo_handle* out) {
   CU_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CU_TRY(h->scal.reserve(16));
   CU_TRY(h->status.reserve(1));
+  // developer knobs (A/B runs): first-pass products and the mbarrier suspend hint of the fused kernels
+  if (const char* e = getenv("B200BO_FAST_PRODUCTS")) h->fast_products = atoi(e) == 3 ? 3 : 1;
+  if (const char* e = getenv("B200BO_WAIT_HINT_NS")) {
+    unsigned v = (unsigned)atoi(e);
+    CU_TRY(cudaMemcpyToSymbol(fk::g_wait_hint_ns, &v, sizeof v));
+  }
   *out = h;
   return 0;
 }
@@ -242,7 +249,7 @@ int b200bo_destroy(b200bo_handle h) {
   h->Lh.release(); h->Ll.release(); h->Xs.release(); h->dbg_w.release();
   h->cscale.release(); h->fvec.release(); h->f_yhat.release(); h->f_sumsq.release(); h->f_dotf.release();
   h->stage[0].release(); h->stage[1].release(); h->Xband.release(); h->band_hiB.release();
-  h->errout.release(); h->band_list.release(); h->band_list0.release(); h->thr_key.release();
+  h->trace.release(); h->errout.release(); h->band_list.release(); h->band_list0.release(); h->thr_key.release();
   h->band_count.release(); h->err_flag.release();
   for (int i = 0; i < 2; ++i) {
     if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
@@ -901,6 +908,12 @@ static int launch_fused(b200bo_handle h, const double* xc_dev, long long m, size
     a.yhat = h->f_yhat.p + out_off; a.sumsq = h->f_sumsq.p + out_off; a.dotf = h->f_dotf.p + out_off;
     a.exch = h->exch2.p;
     a.dbg_w = h->want_dbg_w ? h->dbg_w.p : nullptr;
+    a.trace = nullptr;
+    if (getenv("B200BO_TRACE")) {
+      CU_TRY(h->trace.reserve((size_t)fk2::TRACE_CHUNKS * 8));
+      CU_TRY(cudaMemsetAsync(h->trace.p, 0, (size_t)fk2::TRACE_CHUNKS * 64, h->stream));
+      a.trace = h->trace.p;
+    }
     a.err = h->err_flag.p;
     a.M = m; a.N = h->N; a.D = h->D; a.ld = h->ld; a.corr = h->corr; a.dk_steps = (h->D + 15) / 16; a.beta = h->beta;
     a.out_scale = (float)ldexp(1.0, -(fk::A_SCALE_LOG2 + h->b_scale_log2));
@@ -920,6 +933,22 @@ static int launch_fused(b200bo_handle h, const double* xc_dev, long long m, size
     }
 #undef FK2_LAUNCH
     CU_TRY(cudaGetLastError());
+    if (a.trace) {  // developer timeline: dump the stamps of CTA 0 relative to its first one
+      std::vector<long long> t((size_t)fk2::TRACE_CHUNKS * 8);
+      CU_TRY(cudaMemcpyAsync(t.data(), a.trace, t.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+      CU_TRY(cudaStreamSynchronize(h->stream));
+      if (FILE* f = fopen(getenv("B200BO_TRACE"), "w")) {
+        long long t0 = 0;
+        for (long long v : t) if (v && (!t0 || v < t0)) t0 = v;
+        fprintf(f, "# chunk  mma:wait_A  mma:A_ready  mma:issued | prod:start  prod:G_ready  prod:A_free  prod:stored  prod:after_bar   (cycles, nprod=%d)\n", nprod);
+        for (int c = 0; c < fk2::TRACE_CHUNKS; ++c) {
+          fprintf(f, "%4d", c);
+          for (int k = 0; k < 8; ++k) fprintf(f, " %9lld", t[c * 8 + k] ? t[c * 8 + k] - t0 : -1);
+          fprintf(f, "\n");
+        }
+        fclose(f);
+      }
+    }
     return 0;
   }
   fk::FusedArgs a;

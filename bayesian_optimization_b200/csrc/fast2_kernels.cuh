@@ -36,15 +36,17 @@ constexpr int AX_PLANE = BM * 128;          // candidate tile, 128 rows x 128 B 
 constexpr int NPW = 16;                     // producer warps
 constexpr int PW0 = 8;
 constexpr int NT2 = 32 * (PW0 + NPW);       // 768 threads
-constexpr int X_SCALE_LOG2 = 4;             // coordinates x 16 before the fp16 split
+constexpr int X_SCALE_LOG2 = 4;
+constexpr int TRACE_CHUNKS = 256;             // coordinates x 16 before the fp16 split
 
 constexpr int OFF_A = 0;
 constexpr int OFF_B = OFF_A + A_STAGES * A_STAGE_BYTES;          // 64 KB
 constexpr int OFF_X = OFF_B + B_SLOTS * B_SLOT_BYTES;            // +96 KB
 constexpr int OFF_AX = OFF_X + X_STAGES * X_STAGE_BYTES;         // +34 KB
 constexpr int OFF_AUX = OFF_AX + 2 * AX_PLANE;                   // +32 KB
-constexpr int OFF_BAR = OFF_AUX + X_STAGES * AUX_BYTES;
-constexpr int SMEM_BYTES = OFF_BAR + 256;
+constexpr int AUX_STAGES = 3;                                    // own ring: released by the producers, not by the Gram MMA
+constexpr int OFF_BAR = OFF_AUX + AUX_STAGES * AUX_BYTES;
+constexpr int SMEM_BYTES = OFF_BAR + 320;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 
 struct Fused2Args {
@@ -57,6 +59,7 @@ struct Fused2Args {
   double* dotf;
   float2* exch;          // (gridDim.x, 3, 128) scratch: partial dot products of the column quarters 1..3
   float* dbg_w;
+  long long* trace;      // NULL, or (TRACE_CHUNKS, 8) clock64 stamps of CTA 0 (developer timeline, B200BO_TRACE=1)
   int* err;
   long long M;
   int N, D, ld, corr, dk_steps;  // dk_steps = ceil(D / 16): k-steps of the Gram MMA
@@ -80,16 +83,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 
 // barrier indices
 enum {
-  BAR_FULL_A = 0,    // [2] producers -> MMA (count NPW)
-  BAR_EMPTY_A = 2,   // [2] MMA commit -> producers
-  BAR_FULL_B = 4,    // [3] TMA -> MMA
-  BAR_EMPTY_B = 7,   // [3] MMA commit -> TMA
-  BAR_FULL_X = 10,   // [2] TMA -> MMA
-  BAR_EMPTY_X = 12,  // [2] MMA commit -> TMA
-  BAR_FULL_G = 14,   // [2] MMA commit -> producers
-  BAR_FULL_AX = 16,  // producers -> MMA (count NPW): candidate operand of the Gram MMA written
-  BAR_ACC_FULL = 17, // MMA commit -> epilogue
-  BAR_ACC_EMPTY = 18 // epilogue -> MMA (count 4)
+  BAR_FULL_A = 0,    // [4] producers -> MMA
+  BAR_EMPTY_A = 4,   // [4] MMA commit -> producers
+  BAR_FULL_B = 8,    // [6] TMA -> MMA
+  BAR_EMPTY_B = 14,  // [6] MMA commit -> TMA
+  BAR_FULL_X = 20,   // [2] TMA -> MMA, producers
+  BAR_EMPTY_X = 22,  // [2] MMA commit -> TMA
+  BAR_FULL_G = 24,   // [2] MMA commit -> producers
+  BAR_FULL_AX = 26,  // producers -> MMA: candidate operand of the Gram MMA written
+  BAR_ACC_FULL = 27, // MMA commit -> epilogue
+  BAR_ACC_EMPTY = 28, // epilogue -> MMA (count 4)
+  BAR_FULL_AUX = 29,  // [3] TMA -> producers: (b_j, gamma_j, f_j) of a chunk
+  BAR_EMPTY_AUX = 32  // [3] producers -> TMA
 };
 
 // r * 2^14 from the (clamped) scaled squared distance; CORR is a template parameter so the loop body is branch-free
@@ -115,7 +120,13 @@ predict_fused_tc2_kernel(const __grid_constant__ CUtensorMap map_hi, const __gri
   uint64_t* bars = (uint64_t*)(smem + OFF_BAR);
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
-  uint32_t* tmem_slot = (uint32_t*)(bars + 24);
+  uint32_t* tmem_slot = (uint32_t*)(bars + 36);
+  // A ring: the one-product pass stores only the hi plane, so the same 64 KB hold four stages instead of two
+  constexpr int A_ST = NPROD == 1 ? 4 : 2;
+  constexpr int A_STRIDE = NPROD == 1 ? A_HALF_BYTES : A_STAGE_BYTES;
+  // B ring likewise: six 16 KB slots (each lasts 256 tensor cycles -- the ring must cover the L2 latency) or three 32 KB
+  constexpr int B_ST = NPROD == 1 ? 6 : 3;
+  constexpr int B_STRIDE = NPROD == 1 ? B_PLANE : B_SLOT_BYTES;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ld = p.ld;
@@ -131,20 +142,24 @@ predict_fused_tc2_kernel(const __grid_constant__ CUtensorMap map_hi, const __gri
     tma_prefetch_desc(&map_lo);
     tma_prefetch_desc(&map_xh);
     tma_prefetch_desc(&map_xl);
-    for (int i = 0; i < A_STAGES; ++i) {
-      mbar_init(BAR(BAR_FULL_A + i), NPW);
+    for (int i = 0; i < A_ST; ++i) {
+      mbar_init(BAR(BAR_FULL_A + i), 1);   // one elected producer thread arrives after the producers' named barrier
       mbar_init(BAR(BAR_EMPTY_A + i), 1);
     }
-    for (int i = 0; i < B_SLOTS; ++i) {
+    for (int i = 0; i < B_ST; ++i) {
       mbar_init(BAR(BAR_FULL_B + i), 1);
       mbar_init(BAR(BAR_EMPTY_B + i), 1);
     }
     for (int i = 0; i < X_STAGES; ++i) {
       mbar_init(BAR(BAR_FULL_X + i), 1);
-      mbar_init(BAR(BAR_EMPTY_X + i), 1 + NPW);  // Gram MMA retired + every producer warp has read the aux block
+      mbar_init(BAR(BAR_EMPTY_X + i), 1);
       mbar_init(BAR(BAR_FULL_G + i), 1);
     }
-    mbar_init(BAR(BAR_FULL_AX), NPW);
+    for (int i = 0; i < AUX_STAGES; ++i) {
+      mbar_init(BAR(BAR_FULL_AUX + i), 1);
+      mbar_init(BAR(BAR_EMPTY_AUX + i), 1);
+    }
+    mbar_init(BAR(BAR_FULL_AX), 1);
     mbar_init(BAR(BAR_ACC_FULL), 1);
     mbar_init(BAR(BAR_ACC_EMPTY), 4);
     fence_barrier_init();
@@ -169,11 +184,11 @@ predict_fused_tc2_kernel(const __grid_constant__ CUtensorMap map_hi, const __gri
             for (int j = 0; j < WC / NB; ++j) {
               const int n0 = WC * s + NB * j;
               if (n0 >= ld || k0 >= n0 + NB) continue;  // beyond the matrix / above the diagonal
-              const uint32_t b = it % B_SLOTS, ph = (it / B_SLOTS) & 1;
+              const uint32_t b = it % B_ST, ph = (it / B_ST) & 1;
               mbar_wait(BAR(BAR_EMPTY_B + b), ph ^ 1, p.err, 1);
               mbar_arrive_expect_tx(BAR(BAR_FULL_B + b), NPROD == 3 ? B_SLOT_BYTES : B_PLANE);
-              tma_load_2d(sbase + OFF_B + b * B_SLOT_BYTES, &map_hi, k0, n0, BAR(BAR_FULL_B + b));
-              if (NPROD == 3) tma_load_2d(sbase + OFF_B + b * B_SLOT_BYTES + B_PLANE, &map_lo, k0, n0, BAR(BAR_FULL_B + b));
+              tma_load_2d(sbase + OFF_B + b * B_STRIDE, &map_hi, k0, n0, BAR(BAR_FULL_B + b));
+              if (NPROD == 3) tma_load_2d(sbase + OFF_B + b * B_STRIDE + B_PLANE, &map_lo, k0, n0, BAR(BAR_FULL_B + b));
               ++it;
             }
         }
@@ -187,12 +202,15 @@ predict_fused_tc2_kernel(const __grid_constant__ CUtensorMap map_hi, const __gri
           const int kext = min(ld, WC * (s + 1));
           for (int k0 = 0; k0 < kext; k0 += KC) {
             const uint32_t x = it % X_STAGES, ph = (it / X_STAGES) & 1;
+            const uint32_t ax = it % AUX_STAGES, pax = (it / AUX_STAGES) & 1;
+            mbar_wait(BAR(BAR_EMPTY_AUX + ax), pax ^ 1, p.err, 12);
+            mbar_arrive_expect_tx(BAR(BAR_FULL_AUX + ax), AUX_BYTES);
+            bulk_load_1d(sbase + OFF_AUX + ax * AUX_BYTES, p.aux + (size_t)(k0 / KC) * 3 * KC, AUX_BYTES, BAR(BAR_FULL_AUX + ax));
             mbar_wait(BAR(BAR_EMPTY_X + x), ph ^ 1, p.err, 7);
-            mbar_arrive_expect_tx(BAR(BAR_FULL_X + x), 2 * X_PLANE + AUX_BYTES);
+            mbar_arrive_expect_tx(BAR(BAR_FULL_X + x), 2 * X_PLANE);
             const uint32_t dst = sbase + OFF_X + x * X_STAGE_BYTES;
             tma_load_2d(dst, &map_xh, 0, k0, BAR(BAR_FULL_X + x));
             tma_load_2d(dst + X_PLANE, &map_xl, 0, k0, BAR(BAR_FULL_X + x));
-            bulk_load_1d(sbase + OFF_AUX + x * AUX_BYTES, p.aux + (size_t)(k0 / KC) * 3 * KC, AUX_BYTES, BAR(BAR_FULL_X + x));
             ++it;
           }
         }
@@ -222,31 +240,39 @@ predict_fused_tc2_kernel(const __grid_constant__ CUtensorMap map_hi, const __gri
         umma_commit(BAR(BAR_FULL_G + (i & 1)));
         umma_commit(BAR(BAR_EMPTY_X + x));
       };
+      int chunks_per_tile = 0;
+      for (int s = 0; s < n_super; ++s) chunks_per_tile += min(ld, WC * (s + 1)) / KC;
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++itile) {
         // candidate operand of this tile is in place (and every Gram MMA of the previous tile has retired)
         mbar_wait(BAR(BAR_FULL_AX), itile & 1, p.err, 9);
         tc_fence_after();
         issue_gram(ic);
+        if (chunks_per_tile > 1) issue_gram(ic + 1);
+        int lc = 0;  // chunk index within the tile
         for (int s = 0; s < n_super; ++s) {
           const int kext = min(ld, WC * (s + 1));
           mbar_wait(BAR(BAR_ACC_EMPTY), (ist & 1) ^ 1, p.err, 2);
           tc_fence_after();
-          for (int k0 = 0; k0 < kext; k0 += KC) {
-            const bool last_of_tile = (s == n_super - 1) && (k0 + KC >= kext);
-            if (!last_of_tile) issue_gram(ic + 1);  // run ahead: the producers work on chunk i+1 during main(i)
-            const uint32_t a = ic % A_STAGES, pha = (ic / A_STAGES) & 1;
+          for (int k0 = 0; k0 < kext; k0 += KC, ++lc) {
+            const uint32_t a = ic % A_ST, pha = (ic / A_ST) & 1;
+            const bool tr = p.trace && blockIdx.x == 0 && ic < TRACE_CHUNKS;
+            if (tr) p.trace[ic * 8 + 0] = clock64();
             mbar_wait(BAR(BAR_FULL_A + a), pha, p.err, 3);
             tc_fence_after();
-            const uint64_t da_hi = umma_desc_sw128(sbase + OFF_A + a * A_STAGE_BYTES);
-            const uint64_t da_lo = umma_desc_sw128(sbase + OFF_A + a * A_STAGE_BYTES + A_HALF_BYTES);
+            if (tr) p.trace[ic * 8 + 1] = clock64();
+            // run two chunks ahead: the producers have consumed Gram block ic (they signalled FULL_A), so its TMEM
+            // columns take the Gram product of chunk ic+2 -- queued BEFORE main(ic), it is ready when main(ic) starts
+            if (lc + 2 < chunks_per_tile) issue_gram(ic + 2);
+            const uint64_t da_hi = umma_desc_sw128(sbase + OFF_A + a * A_STRIDE);
+            const uint64_t da_lo = umma_desc_sw128(sbase + OFF_A + a * A_STRIDE + A_HALF_BYTES);
             for (int j = 0; j < WC / NB; ++j) {
               const int n0 = WC * s + NB * j;
               if (n0 >= ld || k0 >= n0 + NB) continue;
-              const uint32_t b = ib % B_SLOTS, phb = (ib / B_SLOTS) & 1;
+              const uint32_t b = ib % B_ST, phb = (ib / B_ST) & 1;
               mbar_wait(BAR(BAR_FULL_B + b), phb, p.err, 4);
               tc_fence_after();
-              const uint64_t db_hi = umma_desc_sw128(sbase + OFF_B + b * B_SLOT_BYTES);
-              const uint64_t db_lo = umma_desc_sw128(sbase + OFF_B + b * B_SLOT_BYTES + B_PLANE);
+              const uint64_t db_hi = umma_desc_sw128(sbase + OFF_B + b * B_STRIDE);
+              const uint64_t db_lo = umma_desc_sw128(sbase + OFF_B + b * B_STRIDE + B_PLANE);
               const uint32_t td = tmem_base + (uint32_t)(NB * j);
 #pragma unroll
               for (int ks = 0; ks < KC / 16; ++ks) {
@@ -261,6 +287,7 @@ predict_fused_tc2_kernel(const __grid_constant__ CUtensorMap map_hi, const __gri
               ++ib;
             }
             umma_commit(BAR(BAR_EMPTY_A + a));
+            if (tr) p.trace[ic * 8 + 2] = clock64();
             ++ic;
           }
           umma_commit(BAR(BAR_ACC_FULL));
@@ -343,8 +370,8 @@ predict_fused_tc2_kernel(const __grid_constant__ CUtensorMap map_hi, const __gri
           *(uint4*)(smem + OFF_AX + AX_PLANE + off) = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
         }
         fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(BAR(BAR_FULL_AX));
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * NPW) : "memory");
+        if (warp == PW0 && lane == 0) mbar_arrive(BAR(BAR_FULL_AX));
       }
       float ysum = 0.f, fsum = 0.f;
       double ysum_d = 0.0, fsum_d = 0.0;
@@ -353,13 +380,16 @@ predict_fused_tc2_kernel(const __grid_constant__ CUtensorMap map_hi, const __gri
         const bool last = s == n_super - 1;
         for (int k0 = 0; k0 < kext; k0 += KC) {
           const uint32_t g = ic & 1;
-          const uint32_t x = ic % X_STAGES;
-          mbar_wait(BAR(BAR_FULL_X + x), (ic / X_STAGES) & 1, p.err, 11);  // aux block landed (TMA -> this thread)
+          const uint32_t ax = ic % AUX_STAGES;
+          const bool tr = p.trace && blockIdx.x == 0 && ic < TRACE_CHUNKS && warp == PW0 && lane == 0;
+          if (tr) p.trace[ic * 8 + 3] = clock64();
+          mbar_wait(BAR(BAR_FULL_AUX + ax), (ic / AUX_STAGES) & 1, p.err, 11);  // aux block landed (TMA -> this thread)
           mbar_wait(BAR(BAR_FULL_G + g), (ic / 2) & 1, p.err, 10);
           tc_fence_after();
+          if (tr) p.trace[ic * 8 + 4] = clock64();
           uint32_t gr[16];
           tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(G_COL0 + KC * g + 16 * kq), gr);
-          const float* aux = (const float*)(smem + OFF_AUX + x * AUX_BYTES) + 16 * kq;
+          const float* aux = (const float*)(smem + OFF_AUX + ax * AUX_BYTES) + 16 * kq;
           float bj[16], gj[16], fj[16];
 #pragma unroll
           for (int i = 0; i < 16; i += 4) {
@@ -369,11 +399,10 @@ predict_fused_tc2_kernel(const __grid_constant__ CUtensorMap map_hi, const __gri
               *(float4*)&fj[i] = *(const float4*)(aux + 2 * KC + i);
             }
           }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(BAR(BAR_EMPTY_X + x));  // aux block is in registers
           tmem_ld_wait();
-          const uint32_t a = ic % A_STAGES, pha = (ic / A_STAGES) & 1;
+          const uint32_t a = ic % A_ST, pha = (ic / A_ST) & 1;
           mbar_wait(BAR(BAR_EMPTY_A + a), pha ^ 1, p.err, 6);
+          if (tr) p.trace[ic * 8 + 5] = clock64();
           float kv[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
@@ -390,7 +419,7 @@ predict_fused_tc2_kernel(const __grid_constant__ CUtensorMap map_hi, const __gri
             fsum_d += (double)fsum;
             ysum = fsum = 0.f;
           }
-          uint8_t* a_hi = smem + OFF_A + a * A_STAGE_BYTES;
+          uint8_t* a_hi = smem + OFF_A + a * A_STRIDE;
           uint8_t* a_lo = a_hi + A_HALF_BYTES;
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
@@ -412,8 +441,14 @@ predict_fused_tc2_kernel(const __grid_constant__ CUtensorMap map_hi, const __gri
           }
           tc_fence_before();    // our tcgen05.ld of the Gram block is ordered before the MMA that reuses it
           fence_proxy_async();  // generic-proxy stores -> visible to the tensor core
-          __syncwarp();
-          if (lane == 0) mbar_arrive(BAR(BAR_FULL_A + a));
+          if (tr) p.trace[ic * 8 + 6] = clock64();
+          // ONE arrival per barrier per chunk: every mbarrier event wakes all sleeping warps of the CTA
+          asm volatile("bar.sync 1, %0;" ::"n"(32 * NPW) : "memory");
+          if (tr) p.trace[ic * 8 + 7] = clock64();
+          if (warp == PW0 && lane == 0) {
+            mbar_arrive(BAR(BAR_FULL_A + a));
+            mbar_arrive(BAR(BAR_EMPTY_AUX + ax));  // the aux block has been read by every producer
+          }
           ++ic;
         }
       }

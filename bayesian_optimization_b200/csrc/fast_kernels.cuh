@@ -108,11 +108,13 @@ __device__ __forceinline__ uint32_t mbar_try_wait_hint(uint32_t bar, uint32_t pa
   return ok;
 }
 // bounded wait: a pipeline bug must not hang the GPU -- flag it and trap (~2 s: 2^17 sleeps of <= 16 us)
+__device__ uint32_t g_wait_hint_ns = 16000u;  // tunable (B200BO_WAIT_HINT_NS); 0 = plain try_wait polling
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err, int code) {
   if (mbar_try_wait(bar, parity)) return;
   uint32_t spins = 0;
   long long t0 = 0;
-  while (!mbar_try_wait_hint(bar, parity, 16000u)) {
+  const uint32_t hint = g_wait_hint_ns;
+  while (!(hint ? mbar_try_wait_hint(bar, parity, hint) : mbar_try_wait(bar, parity))) {
     if ((++spins & 63u) == 0) {  // look at the clock only now and then
       const long long t = clock64();
       if (t0 == 0) t0 = t;
