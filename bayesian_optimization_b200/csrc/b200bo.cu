@@ -17,6 +17,7 @@
 #include "dgemm.cuh"
 #include "fast_kernels.cuh"
 #include "fast2_kernels.cuh"
+#include "fast3_kernels.cuh"
 #include "fit_kernels.cuh"
 #include "predict_kernels.cuh"
 
@@ -130,8 +131,10 @@ struct b200bo_ctx {
   DevBuf<float2> exch2;
   DevBuf<double> cmean;
   CUtensorMap map2_hi, map2_lo, map2_xh, map2_xl;
+  fk3::PairMaps pair_maps;  // third generation: CTA pairs (cta_group::2)
+  bool use_pair = false;
   std::vector<double> xmean;  // per-feature mean of the training set (host copy from set_train)
-  int fast_kernel_pref = 2;   // 2: newest kernel that covers the configuration; 1: force the first-generation kernel
+  int fast_kernel_pref = 3;   // 3: newest kernel that covers the configuration (CTA pairs); 2: single-CTA Gram kernel; 1: first generation
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_used[2] = {nullptr, nullptr};
   bool want_dbg_w = false;
@@ -226,6 +229,7 @@ int b200bo_create(int device, b200bo_handle* out) {
   CU_TRY(h->status.reserve(1));
   // developer knobs (A/B runs): first-pass products and the mbarrier suspend hint of the fused kernels
   if (const char* e = getenv("B200BO_FAST_PRODUCTS")) h->fast_products = atoi(e) == 3 ? 3 : 1;
+  if (const char* e = getenv("B200BO_FAST_KERNEL")) h->fast_kernel_pref = std::max(1, std::min(3, atoi(e)));
   if (const char* e = getenv("B200BO_WAIT_HINT_NS")) {
     unsigned v = (unsigned)atoi(e);
     CU_TRY(cudaMemcpyToSymbol(fk::g_wait_hint_ns, &v, sizeof v));
@@ -281,7 +285,7 @@ int b200bo_set_precision(b200bo_handle h, int prec) {
 
 int b200bo_set_fast_kernel(b200bo_handle h, int generation) {
   CHECK_ARG(h, "handle is NULL");
-  CHECK_ARG(generation == 1 || generation == 2, "generation is 1 or 2");
+  CHECK_ARG(generation >= 1 && generation <= 3, "generation is 1, 2 or 3");
   h->fast_kernel_pref = generation;
   h->fast_ready = false;
   h->calibrated[0] = h->calibrated[1] = false;
@@ -884,6 +888,15 @@ static int ensure_fast_state(b200bo_handle h) {
     if ((rc = make_f16_map(&h->map2_lo, h->Ll.p, ld, ld, fk::KC, fk2::NB))) return rc;
     if ((rc = make_f16_map(&h->map2_xh, h->Xh2.p, 64, ld, 64, fk::KC))) return rc;
     if ((rc = make_f16_map(&h->map2_xl, h->Xl2.p, 64, ld, 64, fk::KC))) return rc;
+    h->use_pair = h->fast_kernel_pref >= 3 && (h->num_sms % 2 == 0);
+    if (h->use_pair) {
+      h->pair_maps.hi128 = h->map2_hi;
+      h->pair_maps.lo128 = h->map2_lo;
+      if ((rc = make_f16_map(&h->pair_maps.hi64, h->Lh.p, ld, ld, fk::KC, 64))) return rc;
+      if ((rc = make_f16_map(&h->pair_maps.lo64, h->Ll.p, ld, ld, fk::KC, 64))) return rc;
+      if ((rc = make_f16_map(&h->pair_maps.xh32, h->Xh2.p, 64, ld, 64, 32))) return rc;
+      if ((rc = make_f16_map(&h->pair_maps.xl32, h->Xl2.p, 64, ld, 64, 32))) return rc;
+    }
   }
   CU_TRY(h->err_flag.reserve(1));
   CU_TRY(cudaMemsetAsync(h->err_flag.p, 0, sizeof(int), st));
@@ -918,19 +931,36 @@ static int launch_fused(b200bo_handle h, const double* xc_dev, long long m, size
     a.M = m; a.N = h->N; a.D = h->D; a.ld = h->ld; a.corr = h->corr; a.dk_steps = (h->D + 15) / 16; a.beta = h->beta;
     a.out_scale = (float)ldexp(1.0, -(fk::A_SCALE_LOG2 + h->b_scale_log2));
     const long long tiles = (m + fk::BM - 1) / fk::BM;
-    const int grid = (int)std::min<long long>(h->num_sms, tiles);
+    const int grid = h->use_pair ? (int)std::min<long long>(h->num_sms, 2 * ((tiles + 1) / 2))
+                                 : (int)std::min<long long>(h->num_sms, tiles);
+#define FK3_LAUNCH(C)                                                                                               \
+  do {                                                                                                             \
+    auto kern = nprod == 1 ? fk3::predict_fused_pair_kernel<C, 1> : fk3::predict_fused_pair_kernel<C, 3>;           \
+    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fk3::SMEM_BYTES));              \
+    kern<<<grid, fk2::NT2, fk3::SMEM_BYTES, h->stream>>>(h->pair_maps, a);                                          \
+  } while (0)
 #define FK2_LAUNCH(C)                                                                                               \
   do {                                                                                                             \
     auto kern = nprod == 1 ? fk2::predict_fused_tc2_kernel<C, 1> : fk2::predict_fused_tc2_kernel<C, 3>;             \
     CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fk2::SMEM_BYTES));              \
     kern<<<grid, fk2::NT2, fk2::SMEM_BYTES, h->stream>>>(h->map2_hi, h->map2_lo, h->map2_xh, h->map2_xl, a);        \
   } while (0)
-    switch (h->corr) {
-      case RBF: FK2_LAUNCH(RBF); break;
-      case MATERN12: FK2_LAUNCH(MATERN12); break;
-      case MATERN32: FK2_LAUNCH(MATERN32); break;
-      default: FK2_LAUNCH(MATERN52); break;
+    if (h->use_pair) {
+      switch (h->corr) {
+        case RBF: FK3_LAUNCH(RBF); break;
+        case MATERN12: FK3_LAUNCH(MATERN12); break;
+        case MATERN32: FK3_LAUNCH(MATERN32); break;
+        default: FK3_LAUNCH(MATERN52); break;
+      }
+    } else {
+      switch (h->corr) {
+        case RBF: FK2_LAUNCH(RBF); break;
+        case MATERN12: FK2_LAUNCH(MATERN12); break;
+        case MATERN32: FK2_LAUNCH(MATERN32); break;
+        default: FK2_LAUNCH(MATERN52); break;
+      }
     }
+#undef FK3_LAUNCH
 #undef FK2_LAUNCH
     CU_TRY(cudaGetLastError());
     if (a.trace) {  // developer timeline: dump the stamps of CTA 0 relative to its first one

@@ -91,8 +91,9 @@ int b200bo_destroy(b200bo_handle h);
 int b200bo_set_stream(b200bo_handle h, void* cuda_stream);
 int b200bo_set_precision(b200bo_handle h, int prec);
 int b200bo_set_keep_R(b200bo_handle h, int keep);
-/* which tensor-core kernel B200BO_PREC_FAST uses: 2 (default) = Gram product on the tensor cores where the kernel
- * is a function of the L2 distance, else generation 1; 1 = always the first-generation kernel (A/B comparisons) */
+/* which tensor-core kernel B200BO_PREC_FAST uses: 3 (default) = CTA pairs (tcgen05 cta_group::2) sharing the B operands;
+ * 2 = single-CTA kernel with the Gram product on the tensor cores; both need a kernel that is a function of the L2
+ * distance, else generation 1 runs; 1 = always the first-generation kernel (A/B comparisons) */
 int b200bo_set_fast_kernel(b200bo_handle h, int generation);
 /* fp16 products per MAC of the first tensor-core pass of b200bo_acq: 1 (default; operands rounded to fp16, ~1e-3 on
  * the variance -- the band it leaves is re-scored in fp64, or the call escalates to 3 when the band is too wide) or

@@ -34,10 +34,11 @@ def make(N, D, corr, corr_id, nugget=1e-6):
     return gp, ora
 
 
-@pytest.mark.parametrize("gen", [1, 2])
+@pytest.mark.parametrize("gen", [1, 2, 3])
 @pytest.mark.parametrize("N,D,corr,corr_id", CASES)
 def test_rt_and_moments(N, D, corr, corr_id, gen):
-    """gen 1: distances on the CUDA cores; gen 2: Gram product on the tensor cores (L2 kernels only)"""
+    """gen 1: distances on the CUDA cores; gen 2: Gram product on the tensor cores (L2 kernels only); gen 3: the
+    same on CTA pairs (tcgen05 cta_group::2)"""
     gp, ora = make(N, D, corr, corr_id)
     gp.engine.set_fast_kernel(gen)
     M = 300  # ragged: not a multiple of the 128-row tile
