@@ -26,6 +26,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "gp_predict_acq_candidates_per_sec"
+# dram__bytes_read.sum + dram__bytes_write.sum of one fused-kernel launch (37888 candidates) from ncu --set full
+NCU_TRAFFIC = {("C3", 1): 23.67e6, ("C3", 3): 43.31e6}
 UNIT = "candidates/s"
 
 
@@ -287,20 +289,28 @@ def run_b200(args, w, params):
         "hbm_frac": value / world * (8 * w.D) / 1e9 / peaks.get("hbm_gbs", 6550.0),
     }
     if fast:
-        # executed tensor work per candidate: 3 fp16 products per MAC over the accumulator super-tiles, blocks above
-        # the diagonal skipped at the kernel's granularity; generation 2 adds the Gram MMAs (64 x 16 ceil(D/16) per chunk)
+        # executed tensor work per candidate: products_per_mac fp16 products per MAC over the accumulator super-tiles
+        # (384 columns = a 256- and a 128-column block; blocks above the diagonal skipped per 64-wide chunk), plus the
+        # Gram MMAs (64 x 16 ceil(D/16) per chunk, always three products).  absolute_exponential runs generation 1
+        # (512-column super-tiles of two 256-column blocks, no Gram MMA).
         ld = -(-w.N // 128) * 128
         gen2 = w.corr != "absolute_exponential"
-        WC_, NB_ = (384, 128) if gen2 else (512, 256)
         mac = 0
-        for s_ in range(-(-ld // WC_)):
-            kext = min(ld, WC_ * (s_ + 1))
-            for j_ in range(WC_ // NB_):
-                n0 = WC_ * s_ + NB_ * j_
-                if n0 < ld:
-                    mac += NB_ * min(kext, -(-(n0 + NB_) // 64) * 64)
-            if gen2:
+        if gen2:
+            for s_ in range(-(-ld // 384)):
+                n0, kext = 384 * s_, min(ld, 384 * (s_ + 1))
+                mac += 256 * min(kext, n0 + 256)
+                if n0 + 256 < ld:
+                    mac += 128 * kext
                 mac += (kext // 64) * 64 * 16 * (-(-w.D // 16))
+        else:
+            for s_ in range(-(-ld // 512)):
+                kext = min(ld, 512 * (s_ + 1))
+                for j_ in range(2):
+                    n0 = 512 * s_ + 256 * j_
+                    if n0 < ld:
+                        mac += 256 * min(kext, n0 + 256)
+        WC_ = 384
         nprod = int(round(kern[8] / args.steps))
         if gen2:  # the Gram MMAs always take three products
             gram = sum((min(ld, WC_ * (s_ + 1)) // 64) * 64 * 16 * (-(-w.D // 16)) for s_ in range(-(-ld // WC_)))
@@ -308,8 +318,11 @@ def run_b200(args, w, params):
         else:
             mac_exec = 3 * mac
         exe = cand_per_launch * 2.0 * mac_exec / (launch_ms * 1e-3) / 1e12
+        # DRAM traffic of the fused kernel from the committed ncu --set full capture (profiles/r01/pair_*_ncu_summary.txt):
+        # per 37888-candidate launch; the fp16 L^-1 copy is read once and then served from L2
+        roofline["traffic"] = NCU_TRAFFIC.get((w.name, nprod))
         roofline.update({
-            "kernel": ("predict_fused_tc2_kernel" if gen2 else "predict_fused_tc_kernel") + " (tcgen05.mma kind::f16, 3 split-fp16 products per MAC, fp32 TMEM accumulators)",
+            "kernel": ("predict_fused_pair_kernel (tcgen05.mma cta_group::2 kind::f16, M=256" if gen2 else "predict_fused_tc_kernel (tcgen05.mma kind::f16, M=128") + ", fp32 TMEM accumulators)",
             "executed_tensor_tflops": exe, "executed_frac": exe / peak,
             "products_per_mac": nprod,
             "note": "achieved counts ALGORITHMIC flops (N^2 per candidate); the tensor pipe executes products_per_mac x that "
