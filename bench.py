@@ -34,7 +34,7 @@ UNIT = "candidates/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="C3")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
@@ -169,7 +169,7 @@ def run_reference(args, w, params):
                                    f"numpy/scipy oracle port of the reference, {cores} BLAS threads"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=REAL_STDOUT, flush=True)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -189,8 +189,6 @@ def run_b200(args, w, params):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL prints its version banner there)
         dist.init_process_group("nccl", device_id=dev)
     M = args.m_per_gpu or w.M_per_gpu
     offset = rank * M
@@ -373,13 +371,26 @@ def run_b200(args, w, params):
                       f"{cores} BLAS threads, {dt:.1f} s",
             "argmax_matches_gpu": [int(i) for i in bi] == cb,
         }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=REAL_STDOUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
+REAL_STDOUT = sys.stdout
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line: route everything libraries print to fd 1 (NCCL's version banner, ...) to
+    stderr and keep a private handle on the real stdout for the result"""
+    global REAL_STDOUT
+    sys.stdout.flush()
+    REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
 def main():
     args = parse()
+    claim_stdout()
     from bayesian_optimization_b200 import workloads as wl
 
     w = wl.WORKLOADS[args.workload]
