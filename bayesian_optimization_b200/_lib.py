@@ -46,6 +46,7 @@ SIGNATURES = {
     "b200bo_set_keep_R": (C.c_int, [C.c_void_p, C.c_int]),
     "b200bo_set_fast_kernel": (C.c_int, [C.c_void_p, C.c_int]),
     "b200bo_set_fast_products": (C.c_int, [C.c_void_p, C.c_int]),
+    "b200bo_set_replay": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "b200bo_set_train": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "b200bo_factor": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double,
                                 C.c_int, C.c_void_p, _dp, _dp, _dp, _ip]),
@@ -137,6 +138,9 @@ class Engine:
 
     def set_fast_kernel(self, generation: int):
         _check(self._lib.b200bo_set_fast_kernel(self._h, int(generation)))
+
+    def set_replay(self, budget_mb: int, max_chunks: int = -1):
+        _check(self._lib.b200bo_set_replay(self._h, int(budget_mb), int(max_chunks)))
 
     def set_fast_products(self, products: int):
         _check(self._lib.b200bo_set_fast_products(self._h, int(products)))

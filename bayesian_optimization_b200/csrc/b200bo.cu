@@ -18,6 +18,7 @@
 #include "fast_kernels.cuh"
 #include "fast2_kernels.cuh"
 #include "fast3_kernels.cuh"
+#include "fast4_kernels.cuh"
 #include "fit_kernels.cuh"
 #include "predict_kernels.cuh"
 
@@ -133,8 +134,14 @@ struct b200bo_ctx {
   CUtensorMap map2_hi, map2_lo, map2_xh, map2_xl;
   fk3::PairMaps pair_maps;  // third generation: CTA pairs (cta_group::2)
   bool use_pair = false;
+  fk4::ReplayMaps replay_maps;  // fourth generation: CTA pairs + r replay from an L2-resident scratch
+  bool use_replay = false;
+  int last_n_store = 0;
+  int replay_max_chunks = -1;   // test knob: cap on the stored chunks per tile (< 0: none)
+  DevBuf<__half> r_scratch;
+  int replay_mb = 64;           // scratch budget (MB): sized to stay in L2 next to the fp16 L^-1; 0 = recompute (generation 3)
   std::vector<double> xmean;  // per-feature mean of the training set (host copy from set_train)
-  int fast_kernel_pref = 3;   // 3: newest kernel that covers the configuration (CTA pairs); 2: single-CTA Gram kernel; 1: first generation
+  int fast_kernel_pref = 4;   // 4: CTA pairs + r replay; 3: CTA pairs; 2: single-CTA Gram kernel; 1: first generation
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_used[2] = {nullptr, nullptr};
   bool want_dbg_w = false;
@@ -229,7 +236,8 @@ int b200bo_create(int device, b200bo_handle* out) {
   CU_TRY(h->status.reserve(1));
   // developer knobs (A/B runs): first-pass products and the mbarrier suspend hint of the fused kernels
   if (const char* e = getenv("B200BO_FAST_PRODUCTS")) h->fast_products = atoi(e) == 3 ? 3 : 1;
-  if (const char* e = getenv("B200BO_FAST_KERNEL")) h->fast_kernel_pref = std::max(1, std::min(3, atoi(e)));
+  if (const char* e = getenv("B200BO_FAST_KERNEL")) h->fast_kernel_pref = std::max(1, std::min(4, atoi(e)));
+  if (const char* e = getenv("B200BO_REPLAY_MB")) h->replay_mb = std::max(0, std::min(4096, atoi(e)));
   if (const char* e = getenv("B200BO_WAIT_HINT_NS")) {
     unsigned v = (unsigned)atoi(e);
     CU_TRY(cudaMemcpyToSymbol(fk::g_wait_hint_ns, &v, sizeof v));
@@ -249,7 +257,7 @@ int b200bo_destroy(b200bo_handle h) {
   h->Xc.release(); h->Kst.release(); h->yhat.release(); h->sumsq.release(); h->dotf.release();
   h->mse.release(); h->params.release(); h->part_val.release(); h->best_val.release(); h->vals.release();
   h->part_idx.release(); h->best_idx.release();
-  h->rs_part.release(); h->Xh2.release(); h->Xl2.release(); h->aux2.release(); h->exch2.release(); h->cmean.release();
+  h->rs_part.release(); h->Xh2.release(); h->Xl2.release(); h->aux2.release(); h->exch2.release(); h->cmean.release(); h->r_scratch.release();
   h->Lh.release(); h->Ll.release(); h->Xs.release(); h->dbg_w.release();
   h->cscale.release(); h->fvec.release(); h->f_yhat.release(); h->f_sumsq.release(); h->f_dotf.release();
   h->stage[0].release(); h->stage[1].release(); h->Xband.release(); h->band_hiB.release();
@@ -285,8 +293,18 @@ int b200bo_set_precision(b200bo_handle h, int prec) {
 
 int b200bo_set_fast_kernel(b200bo_handle h, int generation) {
   CHECK_ARG(h, "handle is NULL");
-  CHECK_ARG(generation >= 1 && generation <= 3, "generation is 1, 2 or 3");
+  CHECK_ARG(generation >= 1 && generation <= 4, "generation is 1, 2, 3 or 4");
   h->fast_kernel_pref = generation;
+  h->fast_ready = false;
+  h->calibrated[0] = h->calibrated[1] = false;
+  return 0;
+}
+
+int b200bo_set_replay(b200bo_handle h, int budget_mb, int max_chunks) {
+  CHECK_ARG(h, "handle is NULL");
+  CHECK_ARG(budget_mb >= 0 && budget_mb <= 4096, "budget_mb out of range");
+  h->replay_mb = budget_mb;
+  h->replay_max_chunks = max_chunks;
   h->fast_ready = false;
   h->calibrated[0] = h->calibrated[1] = false;
   return 0;
@@ -896,6 +914,17 @@ static int ensure_fast_state(b200bo_handle h) {
       if ((rc = make_f16_map(&h->pair_maps.lo64, h->Ll.p, ld, ld, fk::KC, 64))) return rc;
       if ((rc = make_f16_map(&h->pair_maps.xh32, h->Xh2.p, 64, ld, 64, 32))) return rc;
       if ((rc = make_f16_map(&h->pair_maps.xl32, h->Xl2.p, 64, ld, 64, 32))) return rc;
+      // r scratch of the replay kernel: (CTA, chunk, plane) blocks of 128 rows x 64 fp16, capped by the budget
+      const size_t blk = (size_t)fk::BM * fk::KC;  // halves per block (16 KB)
+      const size_t want = (size_t)h->num_sms * (ld / fk::KC) * 2 * blk;
+      const size_t cap = (size_t)h->replay_mb * (1u << 20) / sizeof(__half) / blk * blk;
+      const size_t n_halves = std::min(want, cap);
+      h->use_replay = h->fast_kernel_pref >= 4 && n_halves >= (size_t)h->num_sms * 2 * blk;
+      if (h->use_replay) {
+        CU_TRY(h->r_scratch.reserve(n_halves));
+        h->replay_maps.pm = h->pair_maps;
+        if ((rc = make_f16_map(&h->replay_maps.scr, h->r_scratch.p, fk::KC, (int)(h->r_scratch.n / fk::KC), fk::KC, fk::BM))) return rc;
+      }
     }
   }
   CU_TRY(h->err_flag.reserve(1));
@@ -939,13 +968,33 @@ static int launch_fused(b200bo_handle h, const double* xc_dev, long long m, size
     CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fk3::SMEM_BYTES));              \
     kern<<<grid, fk2::NT2, fk3::SMEM_BYTES, h->stream>>>(h->pair_maps, a);                                          \
   } while (0)
+#define FK4_LAUNCH(C)                                                                                               \
+  do {                                                                                                             \
+    auto kern = nprod == 1 ? fk4::predict_fused_replay_kernel<C, 1> : fk4::predict_fused_replay_kernel<C, 3>;       \
+    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fk3::SMEM_BYTES));              \
+    kern<<<grid, fk2::NT2, fk3::SMEM_BYTES, h->stream>>>(h->replay_maps, a, ra);                                    \
+  } while (0)
 #define FK2_LAUNCH(C)                                                                                               \
   do {                                                                                                             \
     auto kern = nprod == 1 ? fk2::predict_fused_tc2_kernel<C, 1> : fk2::predict_fused_tc2_kernel<C, 3>;             \
     CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fk2::SMEM_BYTES));              \
     kern<<<grid, fk2::NT2, fk2::SMEM_BYTES, h->stream>>>(h->map2_hi, h->map2_lo, h->map2_xh, h->map2_xl, a);        \
   } while (0)
-    if (h->use_pair) {
+    if (h->use_pair && h->use_replay) {
+      fk4::ReplayArgs ra;
+      ra.scratch = h->r_scratch.p;
+      const size_t blk = (size_t)fk::BM * fk::KC;
+      const int planes = nprod == 1 ? 1 : 2;
+      ra.n_store = (int)std::min<size_t>((size_t)(h->ld / fk::KC), h->r_scratch.n / ((size_t)h->num_sms * planes * blk)) & ~1;
+      if (h->replay_max_chunks >= 0) ra.n_store = std::min(ra.n_store, h->replay_max_chunks & ~1);
+      h->last_n_store = ra.n_store;
+      switch (h->corr) {
+        case RBF: FK4_LAUNCH(RBF); break;
+        case MATERN12: FK4_LAUNCH(MATERN12); break;
+        case MATERN32: FK4_LAUNCH(MATERN32); break;
+        default: FK4_LAUNCH(MATERN52); break;
+      }
+    } else if (h->use_pair) {
       switch (h->corr) {
         case RBF: FK3_LAUNCH(RBF); break;
         case MATERN12: FK3_LAUNCH(MATERN12); break;
@@ -961,6 +1010,7 @@ static int launch_fused(b200bo_handle h, const double* xc_dev, long long m, size
       }
     }
 #undef FK3_LAUNCH
+#undef FK4_LAUNCH
 #undef FK2_LAUNCH
     CU_TRY(cudaGetLastError());
     if (a.trace) {  // developer timeline: dump the stamps of CTA 0 relative to its first one

@@ -91,10 +91,16 @@ int b200bo_destroy(b200bo_handle h);
 int b200bo_set_stream(b200bo_handle h, void* cuda_stream);
 int b200bo_set_precision(b200bo_handle h, int prec);
 int b200bo_set_keep_R(b200bo_handle h, int keep);
-/* which tensor-core kernel B200BO_PREC_FAST uses: 3 (default) = CTA pairs (tcgen05 cta_group::2) sharing the B operands;
+/* which tensor-core kernel B200BO_PREC_FAST uses: 4 (default) = CTA pairs + replay of r from an L2-resident scratch;
+ * 3 = CTA pairs (tcgen05 cta_group::2) sharing the B operands, r recomputed per accumulator super-tile;
  * 2 = single-CTA kernel with the Gram product on the tensor cores; both need a kernel that is a function of the L2
  * distance, else generation 1 runs; 1 = always the first-generation kernel (A/B comparisons) */
 int b200bo_set_fast_kernel(b200bo_handle h, int generation);
+/* generation 4 only: the fp16 cross-correlation chunks r[:, k:k+64] of a candidate tile are computed once, kept in a
+ * per-SM scratch of at most budget_mb MB in total (default 64: it has to stay in L2 next to the fp16 L^-1) and replayed
+ * by TMA for every later accumulator super-tile; chunks that do not fit are recomputed.  budget_mb = 0 recomputes
+ * everything (generation 3 behaviour); max_chunks >= 0 additionally caps the stored chunks per tile (test knob). */
+int b200bo_set_replay(b200bo_handle h, int budget_mb, int max_chunks);
 /* fp16 products per MAC of the first tensor-core pass of b200bo_acq: 1 (default; operands rounded to fp16, ~1e-3 on
  * the variance -- the band it leaves is re-scored in fp64, or the call escalates to 3 when the band is too wide) or
  * 3 (split fp16, ~1e-6).  b200bo_predict always uses 3. */
