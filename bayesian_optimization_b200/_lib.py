@@ -47,6 +47,7 @@ SIGNATURES = {
     "b200bo_set_fast_kernel": (C.c_int, [C.c_void_p, C.c_int]),
     "b200bo_set_fast_products": (C.c_int, [C.c_void_p, C.c_int]),
     "b200bo_set_replay": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "b200bo_debug_fused_time": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "b200bo_set_train": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "b200bo_factor": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double,
                                 C.c_int, C.c_void_p, _dp, _dp, _dp, _ip]),
@@ -244,6 +245,13 @@ class Engine:
         _check(self._lib.b200bo_debug_fast_rt(self._h, Xc.ctypes.data, M, rt.ctypes.data, yh.ctypes.data,
                                               ss.ctypes.data, df.ctypes.data))
         return rt, yh, ss, df
+
+    def debug_fused_time(self, Xc: np.ndarray, products: int = 1, reps: int = 3) -> float:
+        """average device ms of the fused tensor-core kernel alone (developer hook)"""
+        Xc = _f64(Xc)
+        out = C.c_double(0.0)
+        _check(self._lib.b200bo_debug_fused_time(self._h, Xc.ctypes.data, Xc.shape[0], int(products), int(reps), C.byref(out)))
+        return out.value
 
     def timings(self) -> np.ndarray:
         t = np.zeros(N_TIMINGS)

@@ -19,6 +19,7 @@
 #include "fast2_kernels.cuh"
 #include "fast3_kernels.cuh"
 #include "fast4_kernels.cuh"
+#include "fast5_kernels.cuh"
 #include "fit_kernels.cuh"
 #include "predict_kernels.cuh"
 
@@ -141,7 +142,8 @@ struct b200bo_ctx {
   DevBuf<__half> r_scratch;
   int replay_mb = 64;           // scratch budget (MB): sized to stay in L2 next to the fp16 L^-1; 0 = recompute (generation 3)
   std::vector<double> xmean;  // per-feature mean of the training set (host copy from set_train)
-  int fast_kernel_pref = 4;   // 4: CTA pairs + r replay; 3: CTA pairs; 2: single-CTA Gram kernel; 1: first generation
+  int fast_kernel_pref = 5;   // 5: CTA pairs, producers decoupled through the scratch; 4: CTA pairs + r replay; 3: CTA pairs; 2: single-CTA Gram kernel; 1: first generation
+  bool use_decoupled = false;
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_used[2] = {nullptr, nullptr};
   bool want_dbg_w = false;
@@ -236,7 +238,7 @@ int b200bo_create(int device, b200bo_handle* out) {
   CU_TRY(h->status.reserve(1));
   // developer knobs (A/B runs): first-pass products and the mbarrier suspend hint of the fused kernels
   if (const char* e = getenv("B200BO_FAST_PRODUCTS")) h->fast_products = atoi(e) == 3 ? 3 : 1;
-  if (const char* e = getenv("B200BO_FAST_KERNEL")) h->fast_kernel_pref = std::max(1, std::min(4, atoi(e)));
+  if (const char* e = getenv("B200BO_FAST_KERNEL")) h->fast_kernel_pref = std::max(1, std::min(5, atoi(e)));
   if (const char* e = getenv("B200BO_REPLAY_MB")) h->replay_mb = std::max(0, std::min(4096, atoi(e)));
   if (const char* e = getenv("B200BO_WAIT_HINT_NS")) {
     unsigned v = (unsigned)atoi(e);
@@ -293,7 +295,7 @@ int b200bo_set_precision(b200bo_handle h, int prec) {
 
 int b200bo_set_fast_kernel(b200bo_handle h, int generation) {
   CHECK_ARG(h, "handle is NULL");
-  CHECK_ARG(generation >= 1 && generation <= 4, "generation is 1, 2, 3 or 4");
+  CHECK_ARG(generation >= 1 && generation <= 5, "generation is 1 .. 5");
   h->fast_kernel_pref = generation;
   h->fast_ready = false;
   h->calibrated[0] = h->calibrated[1] = false;
@@ -918,7 +920,9 @@ static int ensure_fast_state(b200bo_handle h) {
       const size_t blk = (size_t)fk::BM * fk::KC;  // halves per block (16 KB)
       const size_t want = (size_t)h->num_sms * (ld / fk::KC) * 2 * blk;
       const size_t cap = (size_t)h->replay_mb * (1u << 20) / sizeof(__half) / blk * blk;
-      const size_t n_halves = std::min(want, cap);
+      // generation 5 keeps every chunk of a tile (both planes): no budget, the scratch may spill out of L2
+      h->use_decoupled = h->fast_kernel_pref >= 5 && ld >= 512 && want * sizeof(__half) <= ((size_t)4 << 30);
+      const size_t n_halves = h->use_decoupled ? want : std::min(want, cap);
       h->use_replay = h->fast_kernel_pref >= 4 && n_halves >= (size_t)h->num_sms * 2 * blk;
       if (h->use_replay) {
         CU_TRY(h->r_scratch.reserve(n_halves));
@@ -952,8 +956,8 @@ static int launch_fused(b200bo_handle h, const double* xc_dev, long long m, size
     a.dbg_w = h->want_dbg_w ? h->dbg_w.p : nullptr;
     a.trace = nullptr;
     if (getenv("B200BO_TRACE")) {
-      CU_TRY(h->trace.reserve((size_t)fk2::TRACE_CHUNKS * 8));
-      CU_TRY(cudaMemsetAsync(h->trace.p, 0, (size_t)fk2::TRACE_CHUNKS * 64, h->stream));
+      CU_TRY(h->trace.reserve((size_t)fk5::TRACE5_CHUNKS * 8));
+      CU_TRY(cudaMemsetAsync(h->trace.p, 0, (size_t)fk5::TRACE5_CHUNKS * 64, h->stream));
       a.trace = h->trace.p;
     }
     a.err = h->err_flag.p;
@@ -974,15 +978,35 @@ static int launch_fused(b200bo_handle h, const double* xc_dev, long long m, size
     CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fk3::SMEM_BYTES));              \
     kern<<<grid, fk2::NT2, fk3::SMEM_BYTES, h->stream>>>(h->replay_maps, a, ra);                                    \
   } while (0)
+#define FK5_LAUNCH(C)                                                                                               \
+  do {                                                                                                             \
+    auto kern = nprod == 1 ? fk5::predict_fused_decoupled_kernel<C, 1, false> : fk5::predict_fused_decoupled_kernel<C, 3, false>; \
+    if (C == MATERN52 && nprod == 1 && a.trace) kern = fk5::predict_fused_decoupled_kernel<MATERN52, 1, true>; /* developer timeline */ \
+    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fk3::SMEM_BYTES));              \
+    kern<<<grid, fk2::NT2, fk3::SMEM_BYTES, h->stream>>>(h->replay_maps, a, ra);                                    \
+  } while (0)
 #define FK2_LAUNCH(C)                                                                                               \
   do {                                                                                                             \
     auto kern = nprod == 1 ? fk2::predict_fused_tc2_kernel<C, 1> : fk2::predict_fused_tc2_kernel<C, 3>;             \
     CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fk2::SMEM_BYTES));              \
     kern<<<grid, fk2::NT2, fk2::SMEM_BYTES, h->stream>>>(h->map2_hi, h->map2_lo, h->map2_xh, h->map2_xl, a);        \
   } while (0)
-    if (h->use_pair && h->use_replay) {
+    if (h->use_pair && h->use_replay && h->use_decoupled) {
       fk4::ReplayArgs ra;
       ra.scratch = h->r_scratch.p;
+      ra.n_store = h->ld / fk::KC;
+      ra.debug = getenv("B200BO_DEBUG_BITS") ? atoi(getenv("B200BO_DEBUG_BITS")) : 0;  // timing experiments (wrong results)
+      h->last_n_store = ra.n_store;
+      switch (h->corr) {
+        case RBF: FK5_LAUNCH(RBF); break;
+        case MATERN12: FK5_LAUNCH(MATERN12); break;
+        case MATERN32: FK5_LAUNCH(MATERN32); break;
+        default: FK5_LAUNCH(MATERN52); break;
+      }
+    } else if (h->use_pair && h->use_replay) {
+      fk4::ReplayArgs ra;
+      ra.scratch = h->r_scratch.p;
+      ra.debug = 0;
       const size_t blk = (size_t)fk::BM * fk::KC;
       const int planes = nprod == 1 ? 1 : 2;
       ra.n_store = (int)std::min<size_t>((size_t)(h->ld / fk::KC), h->r_scratch.n / ((size_t)h->num_sms * planes * blk)) & ~1;
@@ -1011,17 +1035,18 @@ static int launch_fused(b200bo_handle h, const double* xc_dev, long long m, size
     }
 #undef FK3_LAUNCH
 #undef FK4_LAUNCH
+#undef FK5_LAUNCH
 #undef FK2_LAUNCH
     CU_TRY(cudaGetLastError());
     if (a.trace) {  // developer timeline: dump the stamps of CTA 0 relative to its first one
-      std::vector<long long> t((size_t)fk2::TRACE_CHUNKS * 8);
+      std::vector<long long> t((size_t)fk5::TRACE5_CHUNKS * 8);
       CU_TRY(cudaMemcpyAsync(t.data(), a.trace, t.size() * 8, cudaMemcpyDeviceToHost, h->stream));
       CU_TRY(cudaStreamSynchronize(h->stream));
       if (FILE* f = fopen(getenv("B200BO_TRACE"), "w")) {
         long long t0 = 0;
         for (long long v : t) if (v && (!t0 || v < t0)) t0 = v;
         fprintf(f, "# chunk  mma:wait_A  mma:A_ready  mma:issued | prod:start  prod:G_ready  prod:A_free  prod:stored  prod:after_bar   (cycles, nprod=%d)\n", nprod);
-        for (int c = 0; c < fk2::TRACE_CHUNKS; ++c) {
+        for (int c = 0; c < (h->use_decoupled ? fk5::TRACE5_CHUNKS : fk2::TRACE_CHUNKS); ++c) {
           fprintf(f, "%4d", c);
           for (int k = 0; k < 8; ++k) fprintf(f, " %9lld", t[c * 8 + k] ? t[c * 8 + k] - t0 : -1);
           fprintf(f, "\n");
@@ -1402,6 +1427,38 @@ int b200bo_debug_fast_rt(b200bo_handle h, const double* Xc, int64_t M, float* ou
   if (sumsq) CU_TRY(cudaMemcpyAsync(sumsq, h->f_sumsq.p, (size_t)M * 8, cudaMemcpyDeviceToHost, h->stream));
   if (dotf) CU_TRY(cudaMemcpyAsync(dotf, h->f_dotf.p, (size_t)M * 8, cudaMemcpyDeviceToHost, h->stream));
   CU_TRY(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int b200bo_debug_fused_time(b200bo_handle h, const double* Xc_host, int64_t M, int products, int reps, double* out_ms) {
+  CHECK_ARG(h && Xc_host && out_ms, "NULL argument");
+  if (!h->factored) return set_err(B200BO_E_STATE, "debug_fused_time before a successful factor()");
+  CHECK_ARG(M >= 1 && reps >= 1 && (products == 1 || products == 3), "bad argument");
+  CHECK_ARG(fast_supported(h), "the tensor-core path does not cover this kernel / feature count");
+  CU_TRY(cudaSetDevice(h->device));
+  int rc;
+  if ((rc = ensure_fast_state(h))) return rc;
+  const size_t Mpad = (size_t)round_up((int)M, fk::BM);
+  CU_TRY(h->f_yhat.reserve(Mpad + fk::BM));
+  CU_TRY(h->f_sumsq.reserve(Mpad + fk::BM));
+  CU_TRY(h->f_dotf.reserve(Mpad + fk::BM));
+  CU_TRY(h->stage[0].reserve((size_t)M * h->D));
+  CU_TRY(cudaMemcpyAsync(h->stage[0].p, Xc_host, (size_t)M * h->D * 8, cudaMemcpyHostToDevice, h->stream));
+  cudaEvent_t e0, e1;
+  CU_TRY(cudaEventCreate(&e0));
+  CU_TRY(cudaEventCreate(&e1));
+  if ((rc = launch_fused(h, h->stage[0].p, M, 0, products))) return rc;  // warm-up
+  CU_TRY(cudaEventRecord(e0, h->stream));
+  for (int i = 0; i < reps; ++i)
+    if ((rc = launch_fused(h, h->stage[0].p, M, 0, products))) return rc;
+  CU_TRY(cudaEventRecord(e1, h->stream));
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  if ((rc = check_fast_err(h))) return rc;
+  float ms = 0.f;
+  CU_TRY(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *out_ms = (double)ms / reps;
   return 0;
 }
 

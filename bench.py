@@ -26,8 +26,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "gp_predict_acq_candidates_per_sec"
-# dram__bytes_read.sum + dram__bytes_write.sum of one fused-kernel launch (37888 candidates) from ncu --set full
-NCU_TRAFFIC = {("C3", 1): 23.67e6, ("C3", 3): 43.31e6}
+# dram__bytes_read.sum + dram__bytes_write.sum PER CANDIDATE of the fused kernel (generation 5) from the ncu --set full
+# capture of a 75776-candidate launch (profiles/r01/gen5_ncu_summary.txt): the r scratch (148 MB at C3) does not fit L2
+NCU_TRAFFIC_PER_CAND = {("C3", 1): (2.580312e9 + 643.5e6) / 75776}
 UNIT = "candidates/s"
 
 
@@ -294,7 +295,18 @@ def run_b200(args, w, params):
         ld = -(-w.N // 128) * 128
         gen2 = w.corr != "absolute_exponential"
         mac = 0
-        if gen2:
+        gen5 = gen2 and ld >= 512 and int(os.environ.get("B200BO_FAST_KERNEL", "5")) >= 5
+        if gen5:
+            # generation 5: per 64-wide chunk the 256-column MMA below the diagonal of block 0, a 128-column MMA on
+            # block 1 next to it, block 2 whenever it exists; ONE Gram product per chunk and tile (r is replayed)
+            for s_ in range(-(-ld // 384)):
+                n0, kext = 384 * s_, min(ld, 384 * (s_ + 1))
+                for k0 in range(0, kext, 64):
+                    mac += 64 * (256 if k0 < n0 + 128 else 128 if k0 < n0 + 256 else 0)
+                    if n0 + 256 < ld:
+                        mac += 64 * 128
+            mac += (ld // 64) * 64 * 16 * (-(-w.D // 16))
+        elif gen2:
             for s_ in range(-(-ld // 384)):
                 n0, kext = 384 * s_, min(ld, 384 * (s_ + 1))
                 mac += 256 * min(kext, n0 + 256)
@@ -310,17 +322,22 @@ def run_b200(args, w, params):
                         mac += 256 * min(kext, n0 + 256)
         WC_ = 384
         nprod = int(round(kern[8] / args.steps))
-        if gen2:  # the Gram MMAs always take three products
+        if gen5:
+            gram = (ld // 64) * 64 * 16 * (-(-w.D // 16))
+            mac_exec = nprod * (mac - gram) + 3 * gram
+        elif gen2:  # the Gram MMAs always take three products
             gram = sum((min(ld, WC_ * (s_ + 1)) // 64) * 64 * 16 * (-(-w.D // 16)) for s_ in range(-(-ld // WC_)))
             mac_exec = nprod * (mac - gram) + 3 * gram
         else:
             mac_exec = 3 * mac
         exe = cand_per_launch * 2.0 * mac_exec / (launch_ms * 1e-3) / 1e12
-        # DRAM traffic of the fused kernel from the committed ncu --set full capture (profiles/r01/pair_*_ncu_summary.txt):
-        # per 37888-candidate launch; the fp16 L^-1 copy is read once and then served from L2
-        roofline["traffic"] = NCU_TRAFFIC.get((w.name, nprod))
+        # DRAM traffic of the fused kernel per launch: ncu's per-candidate figure x the candidates of one launch
+        tpc = NCU_TRAFFIC_PER_CAND.get((w.name, nprod)) if gen5 else None
+        roofline["traffic"] = tpc * cand_per_launch if tpc else None
         roofline.update({
-            "kernel": ("predict_fused_pair_kernel (tcgen05.mma cta_group::2 kind::f16, M=256" if gen2 else "predict_fused_tc_kernel (tcgen05.mma kind::f16, M=128") + ", fp32 TMEM accumulators)",
+            "kernel": ("predict_fused_decoupled_kernel (tcgen05.mma cta_group::2 kind::f16, M=256, r computed once per tile and replayed by TMA" if gen5
+                       else "predict_fused_pair_kernel (tcgen05.mma cta_group::2 kind::f16, M=256" if gen2
+                       else "predict_fused_tc_kernel (tcgen05.mma kind::f16, M=128") + ", fp32 TMEM accumulators)",
             "executed_tensor_tflops": exe, "executed_frac": exe / peak,
             "products_per_mac": nprod,
             "note": "achieved counts ALGORITHMIC flops (N^2 per candidate); the tensor pipe executes products_per_mac x that "

@@ -91,7 +91,9 @@ int b200bo_destroy(b200bo_handle h);
 int b200bo_set_stream(b200bo_handle h, void* cuda_stream);
 int b200bo_set_precision(b200bo_handle h, int prec);
 int b200bo_set_keep_R(b200bo_handle h, int keep);
-/* which tensor-core kernel B200BO_PREC_FAST uses: 4 (default) = CTA pairs + replay of r from an L2-resident scratch;
+/* which tensor-core kernel B200BO_PREC_FAST uses: 5 (default) = CTA pairs, every r chunk computed once per tile into a
+ * scratch by producers that run a tile ahead, all A operands by TMA, per-block accumulator drain (N >= 512, else 4);
+ * 4 = CTA pairs + replay of r from an L2-resident scratch, first uses written straight into the A ring;
  * 3 = CTA pairs (tcgen05 cta_group::2) sharing the B operands, r recomputed per accumulator super-tile;
  * 2 = single-CTA kernel with the Gram product on the tensor cores; both need a kernel that is a function of the L2
  * distance, else generation 1 runs; 1 = always the first-generation kernel (A/B comparisons) */
@@ -157,6 +159,10 @@ int b200bo_acq_from_moments(b200bo_handle h, const double* yhat, const double* m
  * What it checks against: solve_triangular(C, r.T) of gpr.py:494. */
 int b200bo_debug_fast_rt(b200bo_handle h, const double* Xc, int64_t M, float* out_rt, double* yhat, double* sumsq,
                          double* dotf);
+
+/* developer hook: average device time (ms, CUDA events on the handle's stream) of `reps` back-to-back launches of the
+ * fused tensor-core kernel alone over M host candidates (no band stage, results discarded); products = 1 or 3. */
+int b200bo_debug_fused_time(b200bo_handle h, const double* Xc_host, int64_t M, int products, int reps, double* out_ms);
 
 /* -- instrumentation ------------------------------------------------------------------------------------
  * CUDA-event timings (ms) of the last predict/acq call, recorded on the handle's stream:

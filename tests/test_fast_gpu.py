@@ -34,12 +34,13 @@ def make(N, D, corr, corr_id, nugget=1e-6):
     return gp, ora
 
 
-@pytest.mark.parametrize("gen", [1, 2, 3, 4, (4, 2), (4, 6), (4, 10)])
+@pytest.mark.parametrize("gen", [1, 2, 3, 4, (4, 2), (4, 6), (4, 10), 5])
 @pytest.mark.parametrize("N,D,corr,corr_id", CASES)
 def test_rt_and_moments(N, D, corr, corr_id, gen):
     """gen 1: distances on the CUDA cores; gen 2: Gram product on the tensor cores (L2 kernels only); gen 3: the
     same on CTA pairs (tcgen05 cta_group::2); gen 4: CTA pairs + replay of r from the scratch (everything stored, or
-    only the first 2 / 6 / 10 chunks of a tile, the rest recomputed)"""
+    only the first 2 / 6 / 10 chunks of a tile, the rest recomputed); gen 5: producers decoupled from the MMA ring (every
+    A operand through the scratch, per-block accumulator drain; N < 512 falls back to gen 4)"""
     gp, ora = make(N, D, corr, corr_id)
     if isinstance(gen, tuple):
         gp.engine.set_replay(64, gen[1])
@@ -81,13 +82,13 @@ def test_fast_predict_tolerance(N, D, corr, corr_id):
     (_lib.ACQ_UCB, [0.1, 0.5, 2.0]),
     (_lib.ACQ_PI, [1e-10, 0.05]),
 ])
-@pytest.mark.parametrize("products", [1, 3, (1, 3)])
+@pytest.mark.parametrize("products", [1, 3, (1, 3), (1, 4)])
 @pytest.mark.parametrize("N,D,corr,corr_id", CASES[:3])
 def test_fast_argmax_is_exact(N, D, corr, corr_id, acq, params, products):
     """products = 1: fp16 operands in the first pass (~1e-3 on the variance), band re-scored in fp64, escalation to
     three products when the band is too wide; products = 3: split fp16 (~1e-6).  Same exactness bar for both."""
     gp, ora = make(N, D, corr, corr_id)
-    if isinstance(products, tuple):  # the recomputing CTA-pair kernel (generation 3) as the first pass
+    if isinstance(products, tuple):  # an earlier CTA-pair kernel (generation 3 / 4) as the first pass
         gp.engine.set_fast_kernel(products[1])
         products = products[0]
     gp.engine.set_fast_products(products)
