@@ -47,6 +47,9 @@ SIGNATURES = {
     "b200bo_set_fast_kernel": (C.c_int, [C.c_void_p, C.c_int]),
     "b200bo_set_fast_products": (C.c_int, [C.c_void_p, C.c_int]),
     "b200bo_set_replay": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "b200bo_gradient": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b200bo_acq_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_double, C.c_double,
+                                  C.c_void_p, C.c_void_p]),
     "b200bo_debug_fused_time": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "b200bo_set_train": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "b200bo_factor": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double,
@@ -245,6 +248,25 @@ class Engine:
         _check(self._lib.b200bo_debug_fast_rt(self._h, Xc.ctypes.data, M, rt.ctypes.data, yh.ctypes.data,
                                               ss.ctypes.data, df.ctypes.data))
         return rt, yh, ss, df
+
+    def gradient(self, Xc: np.ndarray):
+        """(yhat (M,), mse (M,), y_dx (M, D), mse_dx (M, D)) -- gpr.py:537-576 for every row of Xc"""
+        Xc = _f64(Xc)
+        M, D = Xc.shape
+        yh, ms = np.empty(M), np.empty(M)
+        ydx, mdx = np.empty((M, D)), np.empty((M, D))
+        _check(self._lib.b200bo_gradient(self._h, Xc.ctypes.data, M, yh.ctypes.data, ms.ctypes.data, ydx.ctypes.data,
+                                         mdx.ctypes.data))
+        return yh, ms, ydx, mdx
+
+    def acq_grad(self, Xc: np.ndarray, acq_id: int, minimize: bool, plugin: float, param: float):
+        """(value (M,), dx (M, D)) of one acquisition function -- its return_dx=True path for every row of Xc"""
+        Xc = _f64(Xc)
+        M, D = Xc.shape
+        val, dx = np.empty(M), np.empty((M, D))
+        _check(self._lib.b200bo_acq_grad(self._h, Xc.ctypes.data, M, int(acq_id), int(bool(minimize)), float(plugin),
+                                         float(param), val.ctypes.data, dx.ctypes.data))
+        return val, dx
 
     def debug_fused_time(self, Xc: np.ndarray, products: int = 1, reps: int = 3) -> float:
         """average device ms of the fused tensor-core kernel alone (developer hook)"""

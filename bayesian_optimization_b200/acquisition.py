@@ -65,9 +65,20 @@ class AcquisitionFunction(ABC):
 
     def __call__(self, X, return_dx: bool = False):
         if return_dx:
-            raise NotImplementedError("return_dx needs the batched posterior gradient (SURVEY.md §8f rank 1)")
+            # the reference's return_dx path takes one point (model.gradient raises on more, gpr.py:547-548) and
+            # returns (value, dx (1, D)); more rows give (values (M,), dx (M, D)) from one device pass
+            X = self.check_X(X)
+            val, dx = self.value_and_gradient(X)
+            return (val[0], dx) if X.shape[0] == 1 else (val, dx)
         _, _, vals = self._run(X, [self._param()], True)
         return vals[0]
+
+    def value_and_gradient(self, X) -> Tuple[np.ndarray, np.ndarray]:
+        """(values (M,), gradients (M, D)): acquisition_fun.py return_dx=True for every row of X."""
+        X = self.check_X(X)
+        if not getattr(self._model, "is_fitted", False):
+            raise RuntimeError("the model is not fitted")
+        return self._engine().acq_grad(X, self._acq_id, self.minimize, self._plugin_value(), self._param())
 
     def batch(self, X, params: Sequence[float]) -> np.ndarray:
         """Values for q parameter settings from ONE predict pass -> (q, M)."""

@@ -21,6 +21,7 @@
 #include "fast4_kernels.cuh"
 #include "fast5_kernels.cuh"
 #include "fit_kernels.cuh"
+#include "grad_kernels.cuh"
 #include "predict_kernels.cuh"
 
 using namespace b2;
@@ -115,6 +116,8 @@ struct b200bo_ctx {
   DevBuf<long long> part_idx, best_idx;
   // tensor-core (B200BO_PREC_FAST) state, built lazily after factor()
   bool fast_ready = false;
+  bool fvec_ready = false;      // fvec = L^-T Ft of the current factorisation (gradient path)
+  DevBuf<double> gRT, gZ, g_ydx, g_mdx, g_val, g_dx;
   bool calibrated[2] = {false, false};  // [0]: one-product first pass, [1]: three-product pass
   int DP = 0, b_scale_log2 = 0;
   double dy_cal[2] = {0, 0}, ds_cal[2] = {0, 0};
@@ -298,6 +301,7 @@ int b200bo_set_fast_kernel(b200bo_handle h, int generation) {
   CHECK_ARG(generation >= 1 && generation <= 5, "generation is 1 .. 5");
   h->fast_kernel_pref = generation;
   h->fast_ready = false;
+  h->fvec_ready = false;
   h->calibrated[0] = h->calibrated[1] = false;
   return 0;
 }
@@ -308,6 +312,7 @@ int b200bo_set_replay(b200bo_handle h, int budget_mb, int max_chunks) {
   h->replay_mb = budget_mb;
   h->replay_max_chunks = max_chunks;
   h->fast_ready = false;
+  h->fvec_ready = false;
   h->calibrated[0] = h->calibrated[1] = false;
   return 0;
 }
@@ -373,6 +378,7 @@ int b200bo_factor(b200bo_handle h, int corr, const double* theta, int n_theta, i
   const size_t nn = (size_t)ld * ld;
   h->factored = false;
   h->fast_ready = false;
+  h->fvec_ready = false;
   h->calibrated[0] = h->calibrated[1] = false;
   h->escalate = false;
   CU_TRY(h->A.reserve(nn));
@@ -1428,6 +1434,112 @@ int b200bo_debug_fast_rt(b200bo_handle h, const double* Xc, int64_t M, float* ou
   if (dotf) CU_TRY(cudaMemcpyAsync(dotf, h->f_dotf.p, (size_t)M * 8, cudaMemcpyDeviceToHost, h->stream));
   CU_TRY(cudaStreamSynchronize(h->stream));
   return 0;
+}
+
+// fvec = L^-T Ft, so that Ft^T L^-1 v = fvec . v  (gpr.py:571-572 without the second triangular solve)
+static int ensure_fvec(b200bo_handle h) {
+  if (h->fvec_ready) return 0;
+  const int ld = h->ld;
+  cudaStream_t st = h->stream;
+  CU_TRY(h->fvec.reserve(ld));
+  const int gchunks = (ld + 255) / 256;
+  CU_TRY(h->part.reserve((size_t)gchunks * ld));
+  tri_gemvT_partial_kernel<<<dim3((ld + 255) / 256, gchunks), 256, 0, st>>>(h->W.p, ld, ld, h->Ft.p, h->part.p, 256);
+  CU_TRY(cudaGetLastError());
+  colsum_partials_kernel<<<(ld + 255) / 256, 256, 0, st>>>(h->part.p, ld, gchunks, h->fvec.p);
+  CU_TRY(cudaGetLastError());
+  h->fvec_ready = true;
+  return 0;
+}
+
+// posterior moments + gradients of up to GRAD_CHUNK device-resident candidates into the g_* buffers
+constexpr int GRAD_CHUNK = 1024;
+static int grad_chunk(b200bo_handle h, const double* xc_dev, int m) {
+  cudaStream_t st = h->stream;
+  const int D = h->D, ld = h->ld;
+  const int mpad = round_up(m, PC_BM);
+  int rc;
+  if ((rc = ensure_fvec(h))) return rc;
+  const size_t ks_smem = ((size_t)KS_ROWS * D + D) * sizeof(double);
+  if (ks_smem > 48 * 1024)
+    CU_TRY(cudaFuncSetAttribute(kstar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ks_smem));
+  KstarArgs k;
+  k.Xc = xc_dev; k.Xt = h->Xt.p; k.theta = h->theta.p; k.gamma = h->gamma.p;
+  k.Kst = h->Kst.p; k.yhat = h->yhat.p;
+  k.M = m; k.N = h->N; k.D = D; k.ld = ld; k.corr = h->corr; k.beta = h->beta;
+  kstar_kernel<<<mpad / KS_ROWS, 256, ks_smem, st>>>(k);
+  CU_TRY(cudaGetLastError());
+  // rt = r L^-T  (k <= n: L^-1 is lower triangular)                                        gpr.py:564
+  GemmArgs g{};
+  g.A = h->Kst.p; g.lda = ld; g.B = h->W.p; g.ldb = ld; g.C = h->gRT.p; g.ldc = ld;
+  g.sA = g.sB = g.sC = 0; g.K = ld; g.alpha = 1.0; g.beta = 0.0; g.lower_only = 0; g.kb_mode = 0; g.ke_mode = 1;
+  CU_TRY((launch_gemm<GemmCore<64, 64, 32, 32, false, false, 3>, false, false>(h, g, mpad, ld, 1)));
+  // z = rt L^-1 = R^-1 r  (k >= n)
+  g.A = h->gRT.p; g.B = h->W.p; g.C = h->gZ.p; g.kb_mode = 1; g.ke_mode = 0;
+  CU_TRY((launch_gemm<GemmCore<64, 64, 32, 32, false, true, 3>, false, true>(h, g, mpad, ld, 1)));
+  PostGradArgs a;
+  a.Xc = xc_dev; a.Xt = h->Xt.p; a.theta = h->theta.p; a.Kst = h->Kst.p; a.RT = h->gRT.p; a.Z = h->gZ.p;
+  a.gamma = h->gamma.p; a.fv = h->fvec.p; a.Ft = h->Ft.p;
+  a.y_dx = h->g_ydx.p; a.mse_dx = h->g_mdx.p; a.mse = h->mse.p;
+  a.M = m; a.N = h->N; a.D = D; a.ld = ld; a.corr = h->corr; a.estimate_trend = h->estimate_trend;
+  a.sigma2 = h->sigma2; a.G = h->G;
+  const size_t pg_smem = ((size_t)ld + 2 * D) * sizeof(double);
+  if (pg_smem > 48 * 1024)
+    CU_TRY(cudaFuncSetAttribute(post_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pg_smem));
+  post_grad_kernel<<<m, PG_NT, pg_smem, st>>>(a);
+  CU_TRY(cudaGetLastError());
+  return 0;
+}
+
+static int grad_common(b200bo_handle h, const double* Xc, int64_t M, int acq_id, int minimize, double plugin, double par,
+                       double* yhat, double* mse, double* y_dx, double* mse_dx, double* val, double* dx) {
+  CHECK_ARG(h && (Xc || M == 0), "NULL argument");
+  if (!h->factored) return set_err(B200BO_E_STATE, "gradient before a successful factor()");
+  CHECK_ARG(h->corr != CUBIC, "the cubic kernel has no gradient (corr_dx: `pass`, gpr.py:654-655)");
+  CU_TRY(cudaSetDevice(h->device));
+  int rc;
+  if ((rc = ensure_predict_ws(h, 1, false))) return rc;
+  const int D = h->D, ld = h->ld;
+  const size_t rows = (size_t)round_up(GRAD_CHUNK, PC_BM);
+  CU_TRY(h->gRT.reserve(rows * ld));
+  CU_TRY(h->gZ.reserve(rows * ld));
+  CU_TRY(h->g_ydx.reserve(rows * D));
+  CU_TRY(h->g_mdx.reserve(rows * D));
+  CU_TRY(h->g_val.reserve(rows));
+  CU_TRY(h->g_dx.reserve(rows * D));
+  cudaStream_t st = h->stream;
+  for (int64_t a = 0; a < M; a += GRAD_CHUNK) {
+    const int m = (int)std::min<int64_t>(GRAD_CHUNK, M - a);
+    CU_TRY(cudaMemcpyAsync(h->Xc.p, Xc + (size_t)a * D, (size_t)m * D * 8, cudaMemcpyHostToDevice, st));
+    if ((rc = grad_chunk(h, h->Xc.p, m))) return rc;
+    if (acq_id >= 0) {
+      AcqGradArgs g;
+      g.yhat = h->yhat.p; g.mse = h->mse.p; g.y_dx = h->g_ydx.p; g.mse_dx = h->g_mdx.p; g.val = h->g_val.p; g.dx = h->g_dx.p;
+      g.M = m; g.D = D; g.acq = acq_id; g.minimize = minimize; g.sigma2 = h->sigma2; g.plugin = plugin; g.par = par;
+      acq_grad_kernel<<<(m + 127) / 128, 128, 0, st>>>(g);
+      CU_TRY(cudaGetLastError());
+      if (val) CU_TRY(cudaMemcpyAsync(val + a, h->g_val.p, (size_t)m * 8, cudaMemcpyDeviceToHost, st));
+      if (dx) CU_TRY(cudaMemcpyAsync(dx + (size_t)a * D, h->g_dx.p, (size_t)m * D * 8, cudaMemcpyDeviceToHost, st));
+    }
+    if (yhat) CU_TRY(cudaMemcpyAsync(yhat + a, h->yhat.p, (size_t)m * 8, cudaMemcpyDeviceToHost, st));
+    if (mse) CU_TRY(cudaMemcpyAsync(mse + a, h->mse.p, (size_t)m * 8, cudaMemcpyDeviceToHost, st));
+    if (y_dx) CU_TRY(cudaMemcpyAsync(y_dx + (size_t)a * D, h->g_ydx.p, (size_t)m * D * 8, cudaMemcpyDeviceToHost, st));
+    if (mse_dx) CU_TRY(cudaMemcpyAsync(mse_dx + (size_t)a * D, h->g_mdx.p, (size_t)m * D * 8, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));  // Xc staging buffer is reused by the next chunk
+  }
+  return 0;
+}
+
+int b200bo_gradient(b200bo_handle h, const double* Xc, int64_t M, double* yhat, double* mse, double* y_dx, double* mse_dx) {
+  CHECK_ARG(y_dx && mse_dx, "y_dx / mse_dx are NULL");
+  return grad_common(h, Xc, M, -1, 1, 0.0, 0.0, yhat, mse, y_dx, mse_dx, nullptr, nullptr);
+}
+
+int b200bo_acq_grad(b200bo_handle h, const double* Xc, int64_t M, int acq_id, int minimize, double plugin, double param,
+                    double* val, double* dx) {
+  CHECK_ARG(acq_id >= 0 && acq_id <= 3, "unknown acquisition id");
+  CHECK_ARG(val && dx, "val / dx are NULL");
+  return grad_common(h, Xc, M, acq_id, minimize, plugin, param, nullptr, nullptr, nullptr, nullptr, val, dx);
 }
 
 int b200bo_debug_fused_time(b200bo_handle h, const double* Xc_host, int64_t M, int products, int reps, double* out_ms) {

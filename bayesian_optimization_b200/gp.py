@@ -323,6 +323,27 @@ class GaussianProcess:
         return yhat.reshape(-1, 1)
 
 
+    # ---- posterior gradient (gpr.py:537-576) --------------------------------------------------------------
+    def gradient(self, x):
+        """d yhat / dx and d MSE / dx at ONE point: ((D, 1), (D, 1)) exactly as the reference returns them."""
+        x = np.atleast_2d(np.asarray(x, dtype=np.float64))
+        n_eval, nf = x.shape
+        if nf != self.X.shape[1]:
+            raise Exception("x does not have the right size!")
+        if n_eval != 1:
+            raise Exception("x must be a vector!")
+        _, _, ydx, mdx = self.engine.gradient(x)
+        return ydx.reshape(-1, 1), mdx.reshape(-1, 1)
+
+    def gradient_batch(self, X):
+        """The same for every row of X in one device pass: (yhat (M,1), mse (M,1), y_dx (M,D), mse_dx (M,D))."""
+        X = check_array(X)
+        if X.shape[1] != self.X.shape[1]:
+            raise ValueError("The number of features in X should match the number of features used for fit().")
+        yh, ms, ydx, mdx = self.engine.gradient(X)
+        return yh.reshape(-1, 1), ms.reshape(-1, 1), ydx, mdx
+
+
 def _is_basis_trend(mean) -> bool:
     return isinstance(mean, BasisExpansionTrend) or any(
         c.__name__ == "BasisExpansionTrend" for c in type(mean).__mro__

@@ -160,6 +160,17 @@ int b200bo_acq_from_moments(b200bo_handle h, const double* yhat, const double* m
 int b200bo_debug_fast_rt(b200bo_handle h, const double* Xc, int64_t M, float* out_rt, double* yhat, double* sumsq,
                          double* dotf);
 
+/* -- posterior gradient: GaussianProcess.gradient (gpr.py:537-576, corr_dx :600-661), batched -----------------
+ * Row i of y_dx / mse_dx (M, D) is what the reference returns for Xc[i] (it accepts one point per call).  yhat / mse
+ * (M,) may be NULL.  Host pointers.  Kernels: squared_exponential, matern (nu = 1.5), absolute_exponential as upstream
+ * (incl. the all-zero Jacobian when a Matern point coincides with a training point, gpr.py:628-630, :660-661);
+ * Matern-5/2 and -1/2, left unimplemented upstream, from their analytic derivatives; cubic: B200BO_E_ARG. */
+int b200bo_gradient(b200bo_handle h, const double* Xc, int64_t M, double* yhat, double* mse, double* y_dx, double* mse_dx);
+/* acquisition value and gradient, the return_dx=True path of acquisition_fun.py (UCB :139-146, EI :181-188,
+ * EpsilonPI :220-229, MGFI :292-309; early-outs and failures give zeros as upstream): val (M,), dx (M, D). */
+int b200bo_acq_grad(b200bo_handle h, const double* Xc, int64_t M, int acq_id, int minimize, double plugin, double param,
+                    double* val, double* dx);
+
 /* developer hook: average device time (ms, CUDA events on the handle's stream) of `reps` back-to-back launches of the
  * fused tensor-core kernel alone over M host candidates (no band stage, results discarded); products = 1 or 3. */
 int b200bo_debug_fused_time(b200bo_handle h, const double* Xc_host, int64_t M, int products, int reps, double* out_ms);

@@ -471,6 +471,53 @@ def acquisition(acq: int, yhat, mse, sigma2, plugin, par, minimize=True) -> np.n
     raise ValueError(acq)
 
 
+def acquisition_dx(acq: int, yhat, mse, y_dx, mse_dx, sigma2, plugin, par, minimize=True):
+    """Value and gradient of one acquisition function at ONE point (the reference's return_dx=True path).
+    yhat, mse: scalars from predict; y_dx, mse_dx: (D,) from posterior_gradient.  Returns (value, dx (D,)).
+    acquisition_fun.py:66-80 (_gradient: y_dx negated when maximising), UCB :139-146, EI :162-168 (early-out
+    zeros), :181-188, EpsilonPI :220-229, MGFI :274-275 (early-out), :292-309 (failures -> zeros)."""
+    y = np.float64(yhat) if minimize else -np.float64(yhat)  # numpy scalars: x / 0 is inf / nan as in the reference
+    sd = np.sqrt(np.float64(mse))
+    sigma2, plugin, par = np.float64(sigma2), np.float64(plugin), np.float64(par)
+    ydx = np.asarray(y_dx, dtype=np.float64).ravel() * (1.0 if minimize else -1.0)
+    mdx = np.asarray(mse_dx, dtype=np.float64).ravel()
+    D = ydx.size
+    with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+        if acq == ACQ_UCB:
+            return y + par * sd, ydx + par * (mdx / (2.0 * sd))
+        if acq == ACQ_EI:
+            if sd / np.sqrt(sigma2) < 1e-6:
+                return 0.0, np.zeros(D)
+            d = plugin - y
+            z = d / sd
+            cdf, pdf = ndtr(z), np.exp(-(z**2) / 2.0) / _SQRT_2PI
+            return d * cdf + sd * pdf, -ydx * cdf + (mdx / (2.0 * sd)) * pdf
+        if acq == ACQ_PI:
+            coef = 1.0 - par if y > 0 else 1.0 + par
+            z = (plugin - coef * y) / sd
+            pdf = np.exp(-(z**2) / 2.0) / _SQRT_2PI
+            return float(ndtr(z)), -(coef * ydx + z * (mdx / (2.0 * sd))) * pdf / sd
+        if acq == ACQ_MGFI:
+            t = np.float64(min(float(par), 22.36))
+            if np.isclose(sd, 0):
+                return 0.0, np.zeros(D)
+            beta_p = (plugin - (y - t * sd**2.0)) / sd
+            e = t * (plugin - y - 1) + t**2.0 * sd**2.0 / 2.0
+            big = e > math.log(np.finfo(np.float64).max)
+            val = 0.0 if big else float(ndtr(beta_p) * np.exp(e))
+            if not np.isfinite(val):
+                val = 0.0
+            if big:  # exp overflow inside the gradient block raises -> zeros (:305-306)
+                return val, np.zeros(D)
+            sd_dx = mdx / (2.0 * sd)
+            term = np.exp(t * (plugin + t * sd**2.0 / 2 - y - 1))
+            m_prime_dx = ydx - 2.0 * t * sd * sd_dx
+            beta_p_dx = -(m_prime_dx + beta_p * sd_dx) / sd
+            pdf = np.exp(-(beta_p**2) / 2.0) / _SQRT_2PI
+            return val, term * (pdf * beta_p_dx + float(ndtr(beta_p)) * ((t**2) * sd * sd_dx - t * ydx))
+    raise ValueError(acq)
+
+
 def argmax_first(v: np.ndarray) -> int:
     """numpy argmax semantics: first (lowest-index) maximum."""
     return int(np.argmax(v))

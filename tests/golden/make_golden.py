@@ -238,13 +238,65 @@ def fit_full():
     save("fit_full.npz", cases)
 
 
+def acq_grad():
+    """return_dx=True of every acquisition class, one row at a time, next to gp.gradient (the inputs of the device
+    gradient kernels): RBF / Matern-3/2 / absolute_exponential (the kernels corr_dx implements, gpr.py:634-652),
+    ordinary and simple kriging, minimise and maximise; candidates include exact training points (EI / MGFI
+    early-outs, the Matern 0/0 quirk)."""
+    rng = np.random.default_rng(21)
+    N, D, M = 160, 4, 24
+    X = rng.uniform(-1, 2, (N, D))
+    y = np.cos(X).sum(axis=1) + 0.25 * rng.standard_normal(N)
+    y = (y - y.mean()) / y.std()
+    Xc = rng.uniform(-1, 2, (M, D))
+    Xc[:3] = X[:3]
+    theta = np.array([0.4, 0.9, 0.2, 0.6])
+    cases = {}
+    for corr, cn in [(go.CORR_RBF, "rbf"), (go.CORR_MATERN32, "m32"), (go.CORR_ABSEXP, "abs")]:
+        for ok in (True, False):
+            for minimize in (True, False):
+                gp = make_gp(corr, D, go.MODE_NOISY, ok, 1e-3, 0.1)
+                llf = ref_loader.fixed_theta_fit(gp, X, y, theta, 0.8)
+                c = dict(X=X, y=y, Xc=Xc, corr=corr, theta=theta, mode=go.MODE_NOISY, ok=ok, par_last=0.8, nugget=1e-3,
+                         beta_in=0.1, trend=go.TREND_CONSTANT, minimize=minimize, llf=llf, t=1.7, alpha_ucb=0.7, eps=0.03)
+                fs = dict(ei=ns.EI(model=gp, minimize=minimize), ucb=ns.UCB(model=gp, minimize=minimize, alpha=0.7),
+                          mgfi=ns.MGFI(model=gp, minimize=minimize, t=1.7), epi=ns.EpsilonPI(model=gp, minimize=minimize, epsilon=0.03),
+                          mgfi_big=ns.MGFI(model=gp, minimize=minimize, t=30.0))
+                c["plugin"] = float(fs["ei"].plugin)
+                ydx, mdx = [], []
+                vals = {k: [] for k in fs}
+                dxs = {k: [] for k in fs}
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    for x in Xc:
+                        a, b = gp.gradient(x)
+                        ydx.append(a.ravel())
+                        mdx.append(b.ravel())
+                        for k, f in fs.items():
+                            v, dx = f(x, return_dx=True)
+                            vals[k].append(float(np.sum(v)))
+                            dxs[k].append(np.asarray(dx, float).ravel())
+                    yh, ms = gp.predict(Xc, eval_MSE=True)
+                c.update(y_dx=np.array(ydx), mse_dx=np.array(mdx), yhat=yh.ravel(), mse=ms.ravel(),
+                         sigma2=float(np.atleast_1d(gp.sigma2)[0]))
+                for k in fs:
+                    c[k] = np.array(vals[k])
+                    c[k + "_dx"] = np.array(dxs[k])
+                cases[f"{cn}_{'ok' if ok else 'sk'}_{'min' if minimize else 'max'}"] = c
+    save("acq_grad.npz", cases)
+
+
 if __name__ == "__main__":
     if "--fit-only" in sys.argv:
         fit_full()
+        sys.exit(0)
+    if "--acq-grad-only" in sys.argv:
+        acq_grad()
         sys.exit(0)
     appendix_b()
     medium()
     canonical(False)
     fit_full()
+    acq_grad()
     if "--big" in sys.argv:
         canonical(True)

@@ -166,3 +166,31 @@ def test_parameter_recipes():
     np.testing.assert_allclose(go.ucb_alpha_samples(0.5, 4, 42), 1 / (1 + np.exp(0.0 + 0.6 * xi)))
     s = go.annealing_t_schedule(2.0, 0.1, 32)
     assert s[0] == 2.0 and s[-1] * (0.1 / 2.0) ** (1 / 32) == pytest.approx(0.1)
+
+
+ACQ_GRAD = load_golden("acq_grad")
+
+
+@pytest.mark.parametrize("name", sorted(ACQ_GRAD))
+def test_acquisition_gradients(name):
+    """return_dx=True of the reference's acquisition classes (one row at a time) and gp.gradient against the oracle's
+    posterior_gradient + acquisition_dx; the first three candidates are training points (early-outs, Matern 0/0 quirk)."""
+    c = ACQ_GRAD[name]
+    gp = oracle_fit(c)
+    mn = bool(c["minimize"])
+    pl = go.plugin_value(gp.y, mn)
+    assert pl == pytest.approx(float(c["plugin"]), rel=1e-15)
+    for i in range(c["Xc"].shape[0]):
+        ydx, mdx = go.posterior_gradient(gp, c["Xc"][i])
+        np.testing.assert_allclose(ydx.ravel(), c["y_dx"][i], rtol=1e-7, atol=1e-9)
+        np.testing.assert_allclose(mdx.ravel(), c["mse_dx"][i], rtol=1e-6, atol=1e-9)
+        for key, acq, par in (("ei", go.ACQ_EI, 0.0), ("ucb", go.ACQ_UCB, float(c["alpha_ucb"])),
+                              ("mgfi", go.ACQ_MGFI, float(c["t"])), ("mgfi_big", go.ACQ_MGFI, 30.0),
+                              ("epi", go.ACQ_PI, float(c["eps"]))):
+            v, dx = go.acquisition_dx(acq, c["yhat"][i], c["mse"][i], c["y_dx"][i], c["mse_dx"][i], gp.sigma2, pl, par, mn)
+            assert v == pytest.approx(float(c[key][i]), rel=1e-6, abs=1e-300), (key, i)
+            ref = c[key + "_dx"][i]
+            if np.all(np.isfinite(ref)):
+                np.testing.assert_allclose(dx, ref, rtol=1e-6, atol=1e-9 * max(1.0, np.abs(ref).max()), err_msg=f"{key} {i}")
+            else:  # sd = 0 at a training point: the reference divides by it (UCB / PI) and returns nan / inf
+                assert not np.all(np.isfinite(dx)), (key, i)
