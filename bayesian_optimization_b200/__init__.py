@@ -8,11 +8,12 @@ the C ABI of include/b200bo.h); importing this package does not need a GPU, comp
 from . import _lib
 from ._lib import B200BOError, Engine
 from .acquisition import EI, MGFI, PI, UCB, AcquisitionFunction, EpsilonPI, ImprovementBased
+from .candidates import argmax_candidates, sample_candidates
 from .gp import GaussianProcess, resolve_corr
 from .trend import BasisExpansionTrend, constant_trend
 
 __all__ = [
     "GaussianProcess", "Engine", "B200BOError", "EI", "PI", "EpsilonPI", "UCB", "MGFI",
-    "AcquisitionFunction", "ImprovementBased", "constant_trend", "BasisExpansionTrend", "resolve_corr",
+    "AcquisitionFunction", "ImprovementBased", "argmax_candidates", "sample_candidates", "constant_trend", "BasisExpansionTrend", "resolve_corr",
 ]
 __version__ = "0.1.0"
