@@ -54,6 +54,9 @@ SIGNATURES = {
     "b200bo_set_train": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "b200bo_factor": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double,
                                 C.c_int, C.c_void_p, _dp, _dp, _dp, _ip]),
+    "b200bo_factor_restricted": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int,
+                                           C.c_void_p, _dp, _ip]),
+    "b200bo_llf_grad_restricted": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "b200bo_llf_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "b200bo_get_state": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
     "b200bo_predict": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
@@ -171,6 +174,22 @@ class Engine:
             self._h, int(corr), theta.ctypes.data, int(theta.size), int(mode), float(par_last), float(noise_var),
             int(trend), None if b is None else b.ctypes.data, C.byref(llf), C.byref(s2), C.byref(nv), C.byref(st)))
         return llf.value, s2.value, nv.value, st.value
+
+    def factor_restricted(self, corr: int, theta, sigma2: float, noise_var: float = 0.0, trend: int = TREND_CONSTANT,
+                          beta: Optional[Sequence[float]] = None):
+        """log_likelihood_restricted at (theta, sigma2, noise_var) -> (llf, status)"""
+        theta = _f64(theta).ravel()
+        b = None if beta is None else _f64(beta).ravel()
+        llf, st = C.c_double(), C.c_int()
+        _check(self._lib.b200bo_factor_restricted(
+            self._h, int(corr), theta.ctypes.data, int(theta.size), float(sigma2), float(noise_var), int(trend),
+            None if b is None else b.ctypes.data, C.byref(llf), C.byref(st)))
+        return llf.value, st.value
+
+    def llf_grad_restricted(self, n_par: int) -> np.ndarray:
+        g = np.empty(n_par)
+        _check(self._lib.b200bo_llf_grad_restricted(self._h, g.ctypes.data, int(n_par)))
+        return g
 
     def llf_grad(self, n_par: int) -> np.ndarray:
         g = np.empty(n_par)

@@ -116,6 +116,7 @@ struct b200bo_ctx {
   DevBuf<long long> part_idx, best_idx;
   // tensor-core (B200BO_PREC_FAST) state, built lazily after factor()
   bool fast_ready = false;
+  bool restricted = false;      // the last factor() evaluated log_likelihood_restricted
   bool fvec_ready = false;      // fvec = L^-T Ft of the current factorisation (gradient path)
   DevBuf<double> gRT, gZ, g_ydx, g_mdx, g_val, g_dx;
   bool calibrated[2] = {false, false};  // [0]: one-product first pass, [1]: three-product pass
@@ -364,9 +365,9 @@ int b200bo_set_train(b200bo_handle h, const double* X, const double* y, int N, i
   return 0;
 }
 
-int b200bo_factor(b200bo_handle h, int corr, const double* theta, int n_theta, int mode, double par_last,
-                  double noise_var, int trend, const double* beta_or_null, double* out_llf,
-                  double* out_sigma2, double* out_noise_var, int* out_status) {
+static int factor_impl(b200bo_handle h, int corr, const double* theta, int n_theta, int mode, double par_last,
+                       double noise_var, int trend, const double* beta_or_null, double* out_llf,
+                       double* out_sigma2, double* out_noise_var, int* out_status, bool restricted) {
   CHECK_ARG(h && theta, "NULL argument");
   CHECK_ARG(h->N > 0, "set_train first");
   CHECK_ARG(corr >= 0 && corr <= 5, "unknown correlation id");
@@ -538,10 +539,17 @@ int b200bo_factor(b200bo_handle h, int corr, const double* theta, int n_theta, i
     nv = noise_var;
     double s2t = s2 + nv;
     llf = -0.5 * (N * log(two_pi * s2t) + 2.0 * logdet + rr / s2t);
+    if (restricted) {
+      // log_likelihood_restricted, gpr.py:849-870.  p = 1, F = ones: det(F^T F) = N, prod(diag G)^2 = Ft^T Ft.
+      // The simple-kriging branch SUBTRACTS the log-determinant term (:866) -- kept as upstream.
+      if (est) llf = -0.5 * ((N - 1) * log(two_pi * s2t) - log((double)N) + 2.0 * logdet + log(ff) + rr / s2t);
+      else llf = -0.5 * (N * log(two_pi * s2t) - 2.0 * logdet + rr / s2t);
+    }
   }
   int status = B200BO_FIT_OK;
   if (flag || llf != llf) status = B200BO_FIT_NOT_SPD;
   else if (llf > 0) status = B200BO_FIT_REJECTED;  // gpr.py:981-982
+  h->restricted = restricted;
   h->corr = corr; h->mode = mode; h->trend = trend; h->estimate_trend = est; h->n_theta = n_theta;
   h->par_last = par_last;
   h->sigma2 = s2; h->noise_var = nv;
@@ -557,9 +565,78 @@ int b200bo_factor(b200bo_handle h, int corr, const double* theta, int n_theta, i
   return 0;
 }
 
+int b200bo_factor(b200bo_handle h, int corr, const double* theta, int n_theta, int mode, double par_last,
+                  double noise_var, int trend, const double* beta_or_null, double* out_llf,
+                  double* out_sigma2, double* out_noise_var, int* out_status) {
+  CHECK_ARG(mode >= 0 && mode <= 2, "unknown estimation mode");
+  return factor_impl(h, corr, theta, n_theta, mode, par_last, noise_var, trend, beta_or_null, out_llf, out_sigma2,
+                     out_noise_var, out_status, false);
+}
+
+int b200bo_factor_restricted(b200bo_handle h, int corr, const double* theta, int n_theta, double sigma2, double noise_var,
+                             int trend, const double* beta_or_null, double* out_llf, int* out_status) {
+  CHECK_ARG(sigma2 > 0 && noise_var >= 0, "sigma2 must be positive and noise_var non-negative");
+  // every estimation mode of log_likelihood_restricted builds R = (s2 R0 + tau2 I) / (s2 + tau2)   gpr.py:826-839
+  return factor_impl(h, corr, theta, n_theta, B200BO_MODE_NOISY, sigma2, noise_var, trend, beta_or_null, out_llf,
+                     nullptr, nullptr, out_status, true);
+}
+
+static int ensure_fvec(b200bo_handle h);
+
+int b200bo_llf_grad_restricted(b200bo_handle h, double* out_grad, int n_par) {
+  CHECK_ARG(h && out_grad, "NULL argument");
+  if (!h->factored || !h->restricted) return set_err(B200BO_E_STATE, "llf_grad_restricted before a successful factor_restricted()");
+  const int N = h->N, D = h->D, ld = h->ld, nb = ld / NB;
+  CHECK_ARG(n_par >= 1 && n_par <= D + 2, "n_par out of range");
+  if (!corr_has_dtheta(h->corr))
+    return set_err(B200BO_E_ARG, "the reference leaves this kernel's theta-gradient unimplemented (gpr.py:758-768)");
+  CU_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  int rc;
+  if (h->estimate_trend && (rc = ensure_fvec(h))) return rc;
+  GemmArgs g{};  // Rinv = L^-T L^-1 (lower tiles), as in b200bo_llf_grad
+  g.A = h->W.p; g.B = h->W.p; g.C = h->S.p; g.lda = g.ldb = g.ldc = ld; g.K = ld; g.alpha = 1.0; g.beta = 0.0;
+  g.lower_only = 1; g.kb_mode = 2;
+  CU_TRY((launch_gemm<GemmTN, true, true>(h, g, ld, ld, 1)));
+  const int ntiles = nb * (nb + 1) / 2, S = D + 4;
+  CU_TRY(h->part.reserve((size_t)ntiles * S + 2 * S));
+  const double tv = h->sigma2 + h->noise_var;
+  size_t smem = ((size_t)2 * D * NB + ((D + 1) & ~1) + 2 * NB + 8 * S) * sizeof(double);
+  CU_TRY(cudaFuncSetAttribute(llf_grad_traces_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  std::vector<double> r1(S), r2(S, 0.0);
+  double* dout = h->part.p + (size_t)ntiles * S;
+  // pass 1 (gamma):  slot d = 0.5 [ gamma^T dR0_d gamma / tv - sum(Rinv * dR0_d) ]; T1, T2, tr(Rinv), gamma^T gamma
+  // pass 2 (q = L^-T Q = fvec / G, ordinary kriging only):  slot d = 0.5 tv q^T dR0_d q; T2(q), q^T q      gpr.py:880-882
+  for (int pass = 0; pass < (h->estimate_trend ? 2 : 1); ++pass) {
+    GradArgs a;
+    a.Xt = h->Xt.p; a.theta = h->theta.p; a.Rinv = h->S.p; a.partial = h->part.p;
+    a.N = N; a.D = D; a.ld = ld; a.corr = h->corr;
+    if (pass == 0) { a.gamma = h->gamma.p; a.a = 1.0 / tv; a.b = 1.0; }
+    else { a.gamma = h->fvec.p; a.a = tv / (h->G * h->G); a.b = 0.0; }
+    llf_grad_traces_kernel<<<ntiles, 256, smem, st>>>(a);
+    CU_TRY(cudaGetLastError());
+    grad_reduce_kernel<<<S, 1024, 0, st>>>(h->part.p, ntiles, S, dout);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(pass == 0 ? r1.data() : r2.data(), dout, S * 8, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+  }
+  const double T1 = r1[D], T2 = r1[D + 1], trRinv = r1[D + 2], gg = r1[D + 3];
+  const double G2 = h->G * h->G;
+  const double qR0q = h->estimate_trend ? (2.0 * r2[D + 1] + r2[D + 3]) / G2 : 0.0;   // q^T R0 q (T2, gg of pass 2 are in fvec units)
+  const double qq = h->estimate_trend ? r2[D + 3] / G2 : 0.0;
+  // the (N,N,D+2) tensor of gpr.py:885-891: D theta slices (tv dR0/dtheta_d), R0, I -- indexed by the PARAMETER number
+  std::vector<double> v(D + 2);
+  for (int d = 0; d < D; ++d) v[d] = r1[d] + r2[d];
+  v[D] = -0.5 * ((2.0 * T1 + trRinv) / tv - (2.0 * T2 + gg) / (tv * tv) - qR0q);
+  v[D + 1] = -0.5 * (trRinv / tv - gg / (tv * tv) - qq);
+  for (int i = 0; i < n_par; ++i) out_grad[i] = v[i];
+  return 0;
+}
+
 int b200bo_llf_grad(b200bo_handle h, double* out_grad, int n_par) {
   CHECK_ARG(h && out_grad, "NULL argument");
   if (!h->factored) return set_err(B200BO_E_STATE, "llf_grad before a successful factor()");
+  if (h->restricted) return set_err(B200BO_E_STATE, "the last factor() was restricted: use b200bo_llf_grad_restricted");
   const int N = h->N, D = h->D, ld = h->ld, nb = ld / NB, nt = h->n_theta;
   CHECK_ARG(n_par == nt + (h->mode == B200BO_MODE_NOISELESS ? 0 : 1), "n_par does not match the estimation mode");
   if (!corr_has_dtheta(h->corr))

@@ -197,7 +197,38 @@ class GaussianProcess:
             return llf, self.engine.llf_grad(n_par)
         return llf
 
+    def _split_par_restricted(self, par):
+        """gpr.py:826-835: (theta, sigma2, noise_var) per estimation mode"""
+        par = np.asarray(par, dtype=np.float64).ravel()
+        if self.estimation_mode == "noiseless":
+            return par[:-1], float(par[-1]), 0.0
+        if self.estimation_mode == "noisy":
+            return par[:-1], float(par[-1]), float(np.atleast_1d(self.noise_var)[0])
+        return par[:-2], float(par[-2]), float(par[-1])
+
+    def log_likelihood_restricted(self, par, env=None, eval_grad=False):
+        """Restricted (REML) log-likelihood at ``par`` on the device (gpr.py:813-918); -inf when the factorisation
+        fails (:842-847) or exp(llf) > 1 (:872-875).  ``env`` receives sigma2 / noise_var as upstream (:904-906)."""
+        theta, s2, nv = self._split_par_restricted(par)
+        n_par = np.size(par)
+        llf, status = self.engine.factor_restricted(self._corr_id, theta, s2, nv, _lib.TREND_CONSTANT, self._beta_fixed())
+        self._cache = {}
+        if status != _lib.FIT_OK:
+            return (-np.inf, np.zeros((n_par, 1))) if eval_grad else -np.inf
+        if env is not None:
+            env["sigma2"] = s2
+            env["noise_var"] = nv
+        if eval_grad:
+            return llf, self.engine.llf_grad_restricted(n_par).reshape(-1, 1)
+        return llf
+
     def _refactor(self):
+        if getattr(self, "_restricted_par", None) is not None:
+            _, status = self.engine.factor_restricted(self._corr_id, self.theta_, self._restricted_par[0],
+                                                      self._restricted_par[1], _lib.TREND_CONSTANT, self._beta_fixed())
+            if status != _lib.FIT_OK:  # pragma: no cover - the same inputs factored before
+                raise RuntimeError("re-factorisation of a fitted model failed")
+            return
         par = self._par_vector()
         _, _, _, status = self._factor(par)
         if status != _lib.FIT_OK:  # pragma: no cover - the same inputs factored before
@@ -227,11 +258,30 @@ class GaussianProcess:
         self._adopt(theta, None if self.estimation_mode == "noiseless" else float(par_last), env)
         return llf
 
+    def fit_fixed_restricted(self, X, y, theta, sigma2, noise_var=None):
+        """``fit_fixed`` for likelihood="restricted": parameters (theta, sigma2[, noise_var]) as gpr.py:826-835 reads
+        them (noise_var: 0 in "noiseless" mode, the nugget in "noisy" mode, given in "noise_estim" mode)."""
+        assert self.likelihood == "restricted"
+        self.random_state = check_random_state(self.random_state)
+        self._check_data(X, y)
+        theta = np.asarray(theta, dtype=np.float64).ravel()
+        par = np.r_[theta, float(sigma2)] if self.estimation_mode != "noise_estim" else np.r_[theta, float(sigma2), float(noise_var)]
+        env = {}
+        llf = self.log_likelihood_restricted(par, env)
+        self.log_likelihood_ = llf
+        if not np.isfinite(llf):
+            self.is_fitted = False
+            return llf
+        self._adopt(theta, float(sigma2), env)
+        return llf
+
     def _adopt(self, theta, par_last, env):
         self.theta_ = np.asarray(theta, dtype=np.float64)
         self._par_last = par_last
         self.noise_var = env["noise_var"]
-        self.sigma2 = env["sigma2"]
+        self.sigma2 = np.atleast_1d(env["sigma2"])
+        self._restricted_par = ((float(self.sigma2[0]), float(np.atleast_1d(self.noise_var)[0]))
+                                if self.likelihood == "restricted" else None)
         assert len(self.sigma2) == self.y.shape[1]
         if self.estimate_trend:
             self.mean.beta = self.engine.state(_lib.STATE_BETA)  # gpr.py:787

@@ -26,17 +26,16 @@ def hyperparameter_bounds(gp, par_list):
 
 
 def optimize_hyperparameter(gp):
-    if gp.likelihood != "concentrated":
-        raise NotImplementedError('likelihood="restricted" has no device implementation (SURVEY.md §8f rank 4)')
+    restricted = gp.likelihood == "restricted"
     if gp.optimizer != "BFGS":
         raise NotImplementedError('optimizer="CMA" hangs in the reference on Python 3 and is not provided')
 
     par_list, par_len = ["theta"], [len(gp.thetaL)]
-    if gp.estimation_mode == "noisy":
+    if restricted or gp.estimation_mode == "noisy":  # gpr.py:1073-1076
         par_list += ["sigma2"]
         par_len.append(1)
-    if gp.estimation_mode == "noise_estim":
-        par_list += ["alpha"]
+    if gp.estimation_mode == "noise_estim":          # gpr.py:1078-1084
+        par_list += ["noise_var" if restricted else "alpha"]
         par_len.append(1)
 
     bounds = hyperparameter_bounds(gp, par_list)
@@ -48,7 +47,7 @@ def optimize_hyperparameter(gp):
         log10theta0 = (
             log10(gp.theta0) if gp.theta0 is not None else np.random.uniform(log10(gp.thetaL), log10(gp.thetaU))
         )
-    if gp.estimation_mode == "noiseless":
+    if gp.estimation_mode == "noiseless" and not restricted:  # gpr.py:1103-1106
         log10param = log10theta0
     else:
         log10param = np.r_[log10theta0, np.random.uniform(log10bounds[n_theta:, 0], log10bounds[n_theta:, 1])]
@@ -60,7 +59,7 @@ def optimize_hyperparameter(gp):
     def obj_func(log10param):
         gp.eval_count += 1
         param = 10.0 ** np.array(log10param)
-        llf, grad = gp.log_likelihood_concentrated(param, eval_grad=True)
+        llf, grad = (gp.log_likelihood_restricted if restricted else gp.log_likelihood_concentrated)(param, eval_grad=True)
         return -1.0 * llf, -1.0 * np.asarray(grad, dtype=np.float64).ravel()
 
     gp.eval_count = 0
@@ -85,7 +84,8 @@ def optimize_hyperparameter(gp):
 
     optimal_param = 10.0 ** param_opt
     env = {}
-    optimal_llf_value = gp.log_likelihood_concentrated(optimal_param, env)  # leaves the device state AT the optimum
+    # leaves the device state AT the optimum
+    optimal_llf_value = (gp.log_likelihood_restricted if restricted else gp.log_likelihood_concentrated)(optimal_param, env)
     param, i = {}, 0
     for k, name in enumerate(par_list):
         param[name] = optimal_param[i : i + par_len[k]]

@@ -129,6 +129,17 @@ int b200bo_factor(b200bo_handle h, int corr, const double* theta, int n_theta, i
  * (gpr.py:994-1038, incl. its quirks g2/g3).  n_par = n_theta (+1 for NOISY / NOISE_ESTIM). */
 int b200bo_llf_grad(b200bo_handle h, double* out_grad, int n_par);
 
+/* likelihood="restricted": log_likelihood_restricted(par, env, eval_grad) (gpr.py:813-918).  All three estimation
+ * modes build R = (sigma2 R0 + noise_var I) / (sigma2 + noise_var) (:826-839: noise_var = 0, the nugget, or the last
+ * parameter), so the caller passes sigma2 and noise_var explicitly.  exp(llf) > 1 is rejected as -inf (:872-875);
+ * the simple-kriging branch keeps upstream's sign of the log-determinant term (:866).  The factorisation state
+ * (predict, get_state, gradient) is left at these parameters like after b200bo_factor. */
+int b200bo_factor_restricted(b200bo_handle h, int corr, const double* theta, int n_theta, double sigma2, double noise_var,
+                             int trend, const double* beta_or_null, double* out_llf, int* out_status);
+/* its gradient (gpr.py:876-902): out_grad[i] = slice i of [theta_0 .. theta_{D-1}, sigma2, noise_var], i < n_par --
+ * the reference indexes its gradient tensor by the PARAMETER number, also for an isotropic theta. */
+int b200bo_llf_grad_restricted(b200bo_handle h, double* out_grad, int n_par);
+
 int b200bo_get_state(b200bo_handle h, int what, double* out, size_t n_elems);
 
 /* -- GaussianProcess.predict(X, eval_MSE) (gpr.py:424-512) --------------------------------------------

@@ -249,6 +249,60 @@ def fit_fixed(
     return gp
 
 
+def fit_fixed_restricted(X, y, corr: int, theta, sigma2: float, noise_var: float = 0.0, trend: int = TREND_CONSTANT,
+                         beta_fixed=None, eval_grad: bool = False, n_par: Optional[int] = None):
+    """Restricted (REML) log-likelihood at fixed hyper-parameters + the state fit() keeps.  gpr.py:813-918.
+    All three estimation modes build R = (sigma2 R0 + noise_var I) / (sigma2 + noise_var) (:826-839; noise_var = 0,
+    the nugget, or the last parameter), so the mode only decides n_par.  Note the SIGN of the log-determinant term
+    in the simple-kriging branch (:866), kept as is.  With eval_grad: (gp, gradient (n_par,)) per :876-902, whose
+    tensor slices are indexed by the parameter number (the isotropic-theta quirk of SURVEY App. A g3)."""
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64).reshape(X.shape[0], -1)
+    theta = np.asarray(theta, dtype=np.float64).ravel()
+    bf = None if beta_fixed is None else np.asarray(beta_fixed, dtype=np.float64).ravel()
+    gp = OracleGP(X=X, y=y, corr=corr, theta=theta, mode=MODE_NOISY, trend=trend, beta_fixed=bf)
+    N = X.shape[0]
+    R0 = correlation_matrix(corr, theta, X)
+    gp.R0 = R0
+    tv = sigma2 + noise_var
+    R = (sigma2 * R0 + noise_var * np.eye(N)) / tv
+    try:
+        L, Ft, Yt, Q, G, rho = _aux(R, gp)
+    except np.linalg.LinAlgError:
+        return (gp, np.zeros(n_par or theta.size + 1)) if eval_grad else gp
+    F = trend_basis(trend, X)
+    if gp.estimate_trend:
+        p = Ft.shape[1]
+        llf = -0.5 * ((N - p) * np.log(2 * np.pi * tv) - np.log(np.linalg.det(F.T.dot(F))) + 2 * np.log(np.diag(L)).sum()
+                      + np.log(np.diag(G).prod() ** 2) + rho.T.dot(rho) / tv).sum()
+    else:
+        llf = -0.5 * (N * np.log(2 * np.pi * tv) - 2 * np.log(np.diag(L)).sum() + rho.T.dot(rho) / tv).sum()
+    with np.errstate(over="ignore"):
+        gp.llf = float(llf) if not np.exp(llf) > 1 else -np.inf  # :872-875
+    gp.sigma2, gp.noise_var = float(sigma2), float(noise_var)
+    gp.L, gp.Ft, gp.Yt, gp.Q, gp.G, gp.rho = L, Ft, Yt, Q, G, rho
+    gp.beta = solve_triangular(G, Q.T.dot(Yt)) if gp.estimate_trend else bf.reshape(-1, 1)
+    gp.gamma = solve_triangular(L.T, rho).reshape(-1, y.shape[1])
+    if not eval_grad:
+        return gp
+    n_par = n_par or theta.size + 1
+    gamma_ = gp.gamma / tv
+    Cinv = cho_solve((L, True), np.eye(N)) / tv
+    if gp.estimate_trend:
+        t_ = solve_triangular(L.T, Q)
+        term = t_.dot(t_.T)
+    D = X.shape[1]
+    slices = [tv * corr_dtheta(gp, j) for j in range(D)] + [R0, np.eye(N)]
+    grad = np.zeros(n_par)
+    for i in range(n_par):
+        Cg = slices[i]
+        g = np.sum(Cinv * Cg) - float(gamma_.T.dot(Cg).dot(gamma_).sum())
+        if gp.estimate_trend:
+            g -= np.sum(term * Cg)
+        grad[i] = -0.5 * g
+    return gp, grad
+
+
 def corr_dtheta(gp: OracleGP, j: int) -> np.ndarray:
     """dR0/dtheta_j as the reference's ``corr_grad_theta`` defines it (one (N,N) slice of its (N,N,D)
     tensor).  gpr.py:745 (squared differences), :748 (RBF: -diff*R), :753-757 (Matern-3/2 only:

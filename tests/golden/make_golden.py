@@ -286,9 +286,57 @@ def acq_grad():
     save("acq_grad.npz", cases)
 
 
+def restricted():
+    """likelihood="restricted" (gpr.py:813-918): value + gradient at fixed parameters in the three estimation modes
+    (par = [theta, sigma2] or [theta, sigma2, noise_var]), ordinary and simple kriging, then the state fit() would
+    keep (:402-415) and a predict."""
+    rng = np.random.default_rng(31)
+    N, D, M = 150, 3, 16
+    X = rng.uniform(0, 2, (N, D))
+    y = np.sin(2 * X).sum(axis=1) + 0.3 * rng.standard_normal(N)
+    y = (y - y.mean()) / y.std()
+    Xc = rng.uniform(0, 2, (M, D))
+    cases = {}
+    for corr, cn, theta in [(go.CORR_RBF, "rbf", [0.6, 1.2, 0.3]), (go.CORR_MATERN32, "m32", [0.6, 1.2, 0.3]),
+                            (go.CORR_RBF, "rbfiso", [0.7])]:
+        for mode, mn, nug in [(go.MODE_NOISELESS, "nl", None), (go.MODE_NOISY, "ny", 1e-2), (go.MODE_NOISE_ESTIM, "ne", 1e-2)]:
+            for ok in (True, False):
+                gp = make_gp(corr, D, mode, ok, nug, 0.1)
+                gp.likelihood = "restricted"
+                gp._check_data(X, y)
+                sigma2 = 0.7
+                nv = {go.MODE_NOISELESS: 0.0, go.MODE_NOISY: 1e-2, go.MODE_NOISE_ESTIM: 0.05}[mode]
+                par = np.r_[theta, sigma2] if mode != go.MODE_NOISE_ESTIM else np.r_[theta, sigma2, nv]
+                env = {}
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    llf, grad = gp.log_likelihood_restricted(par, env, eval_grad=True)
+                c = dict(X=X, y=y, Xc=Xc, corr=corr, theta=np.asarray(theta, float), mode=mode, ok=ok, sigma2=sigma2,
+                         noise_var=nv, nugget=0.0 if nug is None else nug, beta_in=0.1, trend=go.TREND_CONSTANT,
+                         llf=llf, llf_grad=np.asarray(grad, float).ravel())
+                if np.isfinite(llf):
+                    gp.theta_ = np.asarray(theta, float)
+                    gp.noise_var, gp.sigma2 = env["noise_var"], np.atleast_1d(env["sigma2"])
+                    gp.rho, gp.Yt, gp.C = env["rho"], env["Yt"], env["C"]
+                    if gp.estimate_trend:
+                        gp.Ft, gp.G, gp.Q = env["Ft"], env["G"], env["Q"]
+                    gp.compute_beta_gamma()
+                    with warnings.catch_warnings():
+                        warnings.simplefilter("ignore")
+                        yh, ms = gp.predict(Xc, eval_MSE=True)
+                    c.update(yhat=yh.ravel(), mse=ms.ravel(), beta=np.asarray(gp.mean.beta, float).ravel(), gamma=gp.gamma.ravel())
+                name = f"{cn}_{mn}_{'ok' if ok else 'sk'}"
+                cases[name] = c
+                print(name, llf)
+    save("restricted.npz", cases)
+
+
 if __name__ == "__main__":
     if "--fit-only" in sys.argv:
         fit_full()
+        sys.exit(0)
+    if "--restricted-only" in sys.argv:
+        restricted()
         sys.exit(0)
     if "--acq-grad-only" in sys.argv:
         acq_grad()
@@ -298,5 +346,6 @@ if __name__ == "__main__":
     canonical(False)
     fit_full()
     acq_grad()
+    restricted()
     if "--big" in sys.argv:
         canonical(True)

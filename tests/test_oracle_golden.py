@@ -194,3 +194,29 @@ def test_acquisition_gradients(name):
                 np.testing.assert_allclose(dx, ref, rtol=1e-6, atol=1e-9 * max(1.0, np.abs(ref).max()), err_msg=f"{key} {i}")
             else:  # sd = 0 at a training point: the reference divides by it (UCB / PI) and returns nan / inf
                 assert not np.all(np.isfinite(dx)), (key, i)
+
+
+RESTRICTED = load_golden("restricted")
+
+
+def oracle_restricted(c, eval_grad=False):
+    kw = {}
+    if not bool(c["ok"]):
+        kw["beta_fixed"] = [float(np.ravel(c["beta_in"])[0])]
+    return go.fit_fixed_restricted(c["X"], c["y"], int(c["corr"]), c["theta"], float(c["sigma2"]), float(c["noise_var"]),
+                                   eval_grad=eval_grad, n_par=c["llf_grad"].size, **kw)
+
+
+@pytest.mark.parametrize("name", sorted(RESTRICTED))
+def test_restricted_likelihood(name):
+    """likelihood="restricted" (gpr.py:813-918): value, gradient and the fitted state against the reference"""
+    c = RESTRICTED[name]
+    gp, grad = oracle_restricted(c, eval_grad=True)
+    # the noiseless RBF matrix (no nugget) has condition ~1e16: rho^T rho carries only a few digits
+    loose = "_nl_" in name and "rbf" in name
+    assert gp.llf == pytest.approx(float(c["llf"]), rel=1e-3 if loose else 1e-10)
+    np.testing.assert_allclose(grad, c["llf_grad"], rtol=1e-2 if loose else 1e-7, atol=1e-7 * np.abs(c["llf_grad"]).max())
+    if not loose:
+        yh, ms = go.predict(gp, c["Xc"])
+        np.testing.assert_allclose(yh.ravel(), c["yhat"], rtol=1e-9, atol=1e-10)
+        np.testing.assert_allclose(ms.ravel(), c["mse"], rtol=1e-8, atol=1e-11)
