@@ -10,10 +10,10 @@ from ._lib import B200BOError, Engine
 from .acquisition import EI, MGFI, PI, UCB, AcquisitionFunction, EpsilonPI, ImprovementBased
 from .candidates import argmax_candidates, sample_candidates
 from .gp import GaussianProcess, resolve_corr
-from .trend import BasisExpansionTrend, constant_trend
+from .trend import BasisExpansionTrend, constant_trend, linear_trend, quadratic_trend
 
 __all__ = [
     "GaussianProcess", "Engine", "B200BOError", "EI", "PI", "EpsilonPI", "UCB", "MGFI",
-    "AcquisitionFunction", "ImprovementBased", "argmax_candidates", "sample_candidates", "constant_trend", "BasisExpansionTrend", "resolve_corr",
+    "AcquisitionFunction", "ImprovementBased", "argmax_candidates", "sample_candidates", "constant_trend", "linear_trend", "quadratic_trend", "BasisExpansionTrend", "resolve_corr",
 ]
 __version__ = "0.1.0"

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "libb200bo.so")
 # ids, kept in sync with include/b200bo.h (tests/test_abi.py parses the header and compares)
 CORR_RBF, CORR_MATERN12, CORR_MATERN32, CORR_MATERN52, CORR_ABSEXP, CORR_CUBIC = range(6)
 MODE_NOISELESS, MODE_NOISY, MODE_NOISE_ESTIM = range(3)
-TREND_CONSTANT = 0
+TREND_CONSTANT, TREND_LINEAR, TREND_QUADRATIC = 0, 1, 2
 FIT_OK, FIT_NOT_SPD, FIT_REJECTED = range(3)
 ACQ_EI, ACQ_PI, ACQ_UCB, ACQ_MGFI = range(4)
 HOST, DEVICE = 0, 1
@@ -196,9 +196,11 @@ class Engine:
         _check(self._lib.b200bo_llf_grad(self._h, g.ctypes.data, int(n_par)))
         return g
 
-    def state(self, what: int) -> np.ndarray:
+    def state(self, what: int, p: int = 1) -> np.ndarray:
+        """p: trend basis size of the last factor() (1 for the constant trend)"""
         N = self.N
-        shape = {STATE_L: (N, N), STATE_LINV: (N, N), STATE_R: (N, N), STATE_BETA: (1,), STATE_G: (1,)}.get(what, (N,))
+        shape = {STATE_L: (N, N), STATE_LINV: (N, N), STATE_R: (N, N), STATE_BETA: (p,), STATE_G: (p, p) if p > 1 else (1,),
+                 STATE_FT: (N, p) if p > 1 else (N,)}.get(what, (N,))
         out = np.empty(shape)
         _check(self._lib.b200bo_get_state(self._h, int(what), out.ctypes.data, out.size))
         return out

@@ -23,6 +23,7 @@
 #include "fit_kernels.cuh"
 #include "grad_kernels.cuh"
 #include "predict_kernels.cuh"
+#include "trend_kernels.cuh"
 
 using namespace b2;
 
@@ -110,6 +111,10 @@ struct b200bo_ctx {
   bool factored = false;
   int corr = 0, mode = 0, trend = 0, estimate_trend = 1, n_theta = 0;
   double sigma2 = NAN, noise_var = 0, beta = 0, G = NAN, llf = -INFINITY, par_last = NAN;
+  // linear / quadratic trend (p > 1): basis F, Ft = L^-1 F, FV = L^-T Ft as (ld, 64) row-major; R factor and beta
+  int p = 1;
+  DevBuf<double> FB, FtG, FV, Gm, betav, Vt;
+  std::vector<double> h_G, h_beta, h_Ft;  // host copies: (p, p) row-major, (p,), (N, p) row-major
   // predict workspace
   int Mc = 0;
   DevBuf<double> Xc, Kst, yhat, sumsq, dotf, mse, params, part_val, best_val, vals;
@@ -372,7 +377,9 @@ static int factor_impl(b200bo_handle h, int corr, const double* theta, int n_the
   CHECK_ARG(h->N > 0, "set_train first");
   CHECK_ARG(corr >= 0 && corr <= 5, "unknown correlation id");
   CHECK_ARG(mode >= 0 && mode <= 2, "unknown estimation mode");
-  CHECK_ARG(trend == B200BO_TREND_CONSTANT, "only the constant trend is implemented on device");
+  CHECK_ARG(trend >= B200BO_TREND_CONSTANT && trend <= B200BO_TREND_QUADRATIC, "unknown trend id");
+  CHECK_ARG(trend_p(trend, h->D) <= TR_PMAX, "at most 64 trend basis functions are supported");
+  CHECK_ARG(!(restricted && trend != B200BO_TREND_CONSTANT), "the restricted likelihood is implemented for the constant trend");
   CHECK_ARG(n_theta == 1 || n_theta == h->D, "Length of theta must be 1 or D");
   CU_TRY(cudaSetDevice(h->device));
   const int N = h->N, D = h->D, ld = h->ld, nb = ld / NB;
@@ -521,11 +528,118 @@ static int factor_impl(b200bo_handle h, int corr, const double* theta, int n_the
   for (int k = 0; k < 4; ++k) h->fit_timings[1 + k] = pt.total(k);
   h->fit_timings[5] = launches;
 
-  const double ff = sc[0], logdet = sc[2], rr = sc[3];
+  const double ff = sc[0], logdet = sc[2];
+  double rr = sc[3];
+  const int p = trend_p(trend, D);
+  h->p = p;
+  if (trend != B200BO_TREND_CONSTANT && !flag) {
+    // ---- general basis (gpr.py:800-808): Ft = L^-1 F on the device, thin QR of the (N, p) panel on the host with
+    // LAPACK's Householder conventions (dgeqr2: R_jj = -sign(alpha) ||x||), rho and beta from it, gamma back on device
+    CU_TRY(h->FB.reserve((size_t)ld * TR_PMAX));
+    CU_TRY(h->FtG.reserve((size_t)ld * TR_PMAX));
+    CU_TRY(h->FV.reserve((size_t)ld * TR_PMAX));
+    CU_TRY(h->Gm.reserve((size_t)TR_PMAX * TR_PMAX));
+    CU_TRY(h->betav.reserve(TR_PMAX));
+    trend_basis_kernel<<<(ld * TR_PMAX + 255) / 256, 256, 0, st>>>(h->Xt.p, N, D, ld, trend, p, h->FB.p);
+    CU_TRY(cudaGetLastError());
+    GemmArgs g{};  // Ft(m, c) = sum_{k <= m} W(m, k) F(k, c)
+    g.A = h->W.p; g.lda = ld; g.B = h->FB.p; g.ldb = TR_PMAX; g.C = h->FtG.p; g.ldc = TR_PMAX;
+    g.K = ld; g.alpha = 1.0; g.beta = 0.0; g.ke_mode = 2;
+    CU_TRY((launch_gemm<GemmNN, false, true>(h, g, ld, TR_PMAX, 1)));
+    std::vector<double> ftp((size_t)ld * TR_PMAX), yt(ld);
+    CU_TRY(cudaMemcpyAsync(ftp.data(), h->FtG.p, ftp.size() * 8, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(yt.data(), h->Yt.p, (size_t)ld * 8, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    h->h_Ft.assign((size_t)N * p, 0.0);
+    for (int i = 0; i < N; ++i)
+      for (int c = 0; c < p; ++c) h->h_Ft[(size_t)i * p + c] = ftp[(size_t)i * TR_PMAX + c];
+    std::vector<double> rho(ld, 0.0);
+    h->h_beta.assign(p, 0.0);
+    h->h_G.assign((size_t)p * p, 0.0);
+    if (est) {
+      // Householder QR in place on a column-major copy; the reflectors are applied to Yt as they are formed
+      std::vector<double> a((size_t)N * p), qty(yt.begin(), yt.begin() + N), tau(p, 0.0);
+      for (int c = 0; c < p; ++c)
+        for (int i = 0; i < N; ++i) a[(size_t)c * N + i] = h->h_Ft[(size_t)i * p + c];
+      for (int j = 0; j < p && j < N; ++j) {
+        double* x = &a[(size_t)j * N];
+        double xn2 = 0.0;
+        for (int i = j + 1; i < N; ++i) xn2 += x[i] * x[i];
+        const double alpha = x[j];
+        if (xn2 == 0.0) {
+          tau[j] = 0.0;
+        } else {
+          const double bt = -copysign(sqrt(alpha * alpha + xn2), alpha);
+          tau[j] = (bt - alpha) / bt;
+          const double sc_ = 1.0 / (alpha - bt);
+          for (int i = j + 1; i < N; ++i) x[i] *= sc_;
+          x[j] = bt;
+        }
+        auto apply = [&](double* col) {  // col <- (I - tau v v^T) col, v = [1, x[j+1:]]
+          double w = col[j];
+          for (int i = j + 1; i < N; ++i) w += x[i] * col[i];
+          w *= tau[j];
+          col[j] -= w;
+          for (int i = j + 1; i < N; ++i) col[i] -= w * x[i];
+        };
+        if (tau[j] != 0.0) {
+          for (int c = j + 1; c < p; ++c) apply(&a[(size_t)c * N]);
+          apply(qty.data());
+        }
+      }
+      for (int i = 0; i < p; ++i)
+        for (int c = i; c < p; ++c) h->h_G[(size_t)i * p + c] = a[(size_t)c * N + i];
+      // beta = G^-1 (Q^T Yt)[:p]                                                        gpr.py:787
+      for (int i = p - 1; i >= 0; --i) {
+        double v = qty[i];
+        for (int c = i + 1; c < p; ++c) v -= h->h_G[(size_t)i * p + c] * h->h_beta[c];
+        h->h_beta[i] = v / h->h_G[(size_t)i * p + i];
+      }
+      // rho = Yt - Q Q^T Yt = Q [0; (Q^T Yt)[p:]]                                       gpr.py:806
+      std::vector<double> r(qty);
+      for (int i = 0; i < p; ++i) r[i] = 0.0;
+      for (int j = std::min(p, N) - 1; j >= 0; --j) {
+        if (tau[j] == 0.0) continue;
+        const double* x = &a[(size_t)j * N];
+        double w = r[j];
+        for (int i = j + 1; i < N; ++i) w += x[i] * r[i];
+        w *= tau[j];
+        r[j] -= w;
+        for (int i = j + 1; i < N; ++i) r[i] -= w * x[i];
+      }
+      for (int i = 0; i < N; ++i) rho[i] = r[i];
+    } else {
+      for (int c = 0; c < p; ++c) h->h_beta[c] = beta_or_null[c];
+      for (int i = 0; i < N; ++i) {                                                       // gpr.py:808
+        double v = yt[i];
+        for (int c = 0; c < p; ++c) v -= h->h_Ft[(size_t)i * p + c] * h->h_beta[c];
+        rho[i] = v;
+      }
+    }
+    rr = 0.0;
+    for (int i = 0; i < N; ++i) rr += rho[i] * rho[i];
+    std::vector<double> gpad((size_t)TR_PMAX * TR_PMAX, 0.0), bpad(TR_PMAX, 0.0);
+    for (int i = 0; i < p; ++i) {
+      bpad[i] = h->h_beta[i];
+      for (int c = 0; c < p; ++c) gpad[(size_t)i * TR_PMAX + c] = h->h_G[(size_t)i * p + c];
+    }
+    CU_TRY(cudaMemcpyAsync(h->rho.p, rho.data(), (size_t)ld * 8, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(h->Gm.p, gpad.data(), gpad.size() * 8, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(h->betav.p, bpad.data(), bpad.size() * 8, cudaMemcpyHostToDevice, st));
+    tri_gemvT_partial_kernel<<<dim3((ld + 255) / 256, gchunks), 256, 0, st>>>(h->W.p, ld, ld, h->rho.p, h->part.p, 256);
+    CU_TRY(cudaGetLastError());
+    colsum_partials_kernel<<<(ld + 255) / 256, 256, 0, st>>>(h->part.p, ld, gchunks, h->gamma.p);
+    CU_TRY(cudaGetLastError());
+    GemmArgs v{};  // FV(n, c) = sum_{k >= n} W(k, n) Ft(k, c)
+    v.A = h->W.p; v.lda = ld; v.B = h->FtG.p; v.ldb = TR_PMAX; v.C = h->FV.p; v.ldc = TR_PMAX;
+    v.K = ld; v.alpha = 1.0; v.beta = 0.0; v.kb_mode = 2;
+    CU_TRY((launch_gemm<GemmTN, true, true>(h, v, ld, TR_PMAX, 1)));
+    CU_TRY(cudaStreamSynchronize(st));
+  }
   double llf, s2, nv;
   const double two_pi = 6.283185307179586;
   if (mode == B200BO_MODE_NOISELESS) {  // gpr.py:932-945
-    int k = est ? 1 : 0;                // rank(Q Q^T) for the p = 1 basis
+    int k = est ? p : 0;                // rank(Q Q^T) = p for a full-rank basis
     s2 = rr / (N - k);
     nv = 0.0;
     llf = -0.5 * (N * log(two_pi * s2) + 2.0 * logdet + N);
@@ -553,7 +667,7 @@ static int factor_impl(b200bo_handle h, int corr, const double* theta, int n_the
   h->corr = corr; h->mode = mode; h->trend = trend; h->estimate_trend = est; h->n_theta = n_theta;
   h->par_last = par_last;
   h->sigma2 = s2; h->noise_var = nv;
-  h->beta = est ? sc[4] : beta_fixed;
+  h->beta = trend != B200BO_TREND_CONSTANT ? 0.0 : (est ? sc[4] : beta_fixed);  // p > 1: added by trend_mse_kernel
   // LAPACK dgeqrf sign convention for the 1x1 R factor: -sign(Ft[0]) * ||Ft||  (gpr.py:805)
   h->G = (ft0 >= 0 ? -1.0 : 1.0) * sqrt(ff);
   h->llf = status == B200BO_FIT_OK ? llf : -INFINITY;
@@ -713,13 +827,29 @@ int b200bo_get_state(b200bo_handle h, int what, double* out, size_t n_elems) {
     case B200BO_STATE_R: return copy_mat(h->Rkeep.p);
     case B200BO_STATE_GAMMA: return copy_vec(h->gamma.p);
     case B200BO_STATE_YT: return copy_vec(h->Yt.p);
-    case B200BO_STATE_FT: return copy_vec(h->Ft.p);
+    case B200BO_STATE_FT:
+      if (h->trend != B200BO_TREND_CONSTANT) {
+        CHECK_ARG(n_elems == (size_t)N * h->p, "expected N*p elements");
+        for (size_t i = 0; i < n_elems; ++i) out[i] = h->h_Ft[i];
+        return 0;
+      }
+      return copy_vec(h->Ft.p);
     case B200BO_STATE_RHO: return copy_vec(h->rho.p);
     case B200BO_STATE_BETA:
+      if (h->trend != B200BO_TREND_CONSTANT) {
+        CHECK_ARG(n_elems == (size_t)h->p, "expected p elements");
+        for (int i = 0; i < h->p; ++i) out[i] = h->h_beta[i];
+        return 0;
+      }
       CHECK_ARG(n_elems == 1, "expected 1 element");
       out[0] = h->beta;
       return 0;
     case B200BO_STATE_G:
+      if (h->trend != B200BO_TREND_CONSTANT) {
+        CHECK_ARG(n_elems == (size_t)h->p * h->p, "expected p*p elements");
+        for (size_t i = 0; i < n_elems; ++i) out[i] = h->h_G[i];
+        return 0;
+      }
       CHECK_ARG(n_elems == 1, "expected 1 element");
       out[0] = h->G;
       return 0;
@@ -787,10 +917,10 @@ static int fp64_moments(b200bo_handle h, const double* xc_dev, int m, double* yh
 // acquisition + arg-max of m candidates whose moments are in (yh, h->sumsq, h->dotf); merges into h->best_*
 static int acq_stage(b200bo_handle h, const double* yh, int m, long long idx_base, const long long* idx_map,
                      int acq_id, int minimize, double plugin, int q, double* vals, long long vals_ld,
-                     long long vals_off, double* mse_out, LaunchCount* lc) {
+                     long long vals_off, double* mse_out, LaunchCount* lc, const double* mse_in = nullptr) {
   cudaStream_t st = h->stream;
   AcqArgs g{};
-  g.yhat = yh; g.sumsq = h->sumsq.p; g.dotf = h->dotf.p; g.mse_in = nullptr; g.mse_out = mse_out;
+  g.yhat = yh; g.sumsq = h->sumsq.p; g.dotf = h->dotf.p; g.mse_in = mse_in; g.mse_out = mse_in ? nullptr : mse_out;
   g.M = m; g.estimate_trend = h->estimate_trend; g.sigma2 = h->sigma2; g.G = h->G;
   g.idx_base = idx_base; g.idx_map = idx_map;
   g.vals = vals; g.vals_ld = vals_ld; g.vals_off = vals_off;
@@ -802,6 +932,28 @@ static int acq_stage(b200bo_handle h, const double* yh, int m, long long idx_bas
   argmax_merge_kernel<<<(q + 63) / 64, 64, 0, st>>>(h->part_val.p, h->part_idx.p, nblk, q, h->best_val.p, h->best_idx.p);
   CU_TRY(cudaGetLastError());
   lc->all += 2;
+  return 0;
+}
+
+// p > 1 trend: yhat += f(x)^T beta, MSE with the p-vector u (gpr.py:490, :496-510); mse_dev may be NULL (mean only)
+static int trend_finish(b200bo_handle h, const double* xc_dev, int m, double* yh, double* mse_dev, LaunchCount* lc) {
+  cudaStream_t st = h->stream;
+  const int ld = h->ld, mpad = round_up(m, PC_BM);
+  if (mse_dev && h->estimate_trend) {
+    CU_TRY(h->Vt.reserve((size_t)round_up(h->Mc, PC_BM) * TR_PMAX));
+    GemmArgs g{};  // Vt(m, c) = sum_k r(m, k) FV(k, c) = (Ft^T rt)_c
+    g.A = h->Kst.p; g.lda = ld; g.B = h->FV.p; g.ldb = TR_PMAX; g.C = h->Vt.p; g.ldc = TR_PMAX;
+    g.K = ld; g.alpha = 1.0; g.beta = 0.0;
+    CU_TRY((launch_gemm<GemmNN, false, true>(h, g, mpad, TR_PMAX, 1)));
+    ++lc->all;
+  }
+  TrendMseArgs a;
+  a.Xc = xc_dev; a.Vt = h->Vt.p; a.sumsq = h->sumsq.p; a.Gm = h->Gm.p; a.beta = h->betav.p; a.yhat = yh; a.mse = mse_dev;
+  a.M = m; a.D = h->D; a.trend = h->trend; a.p = h->p; a.estimate_trend = h->estimate_trend; a.sigma2 = h->sigma2;
+  const size_t smem = ((size_t)h->p * h->p + h->p) * sizeof(double);
+  trend_mse_kernel<<<(m + 127) / 128, 128, smem, st>>>(a);
+  CU_TRY(cudaGetLastError());
+  ++lc->all;
   return 0;
 }
 
@@ -852,13 +1004,21 @@ static int run_candidates_fp64(b200bo_handle h, const double* Xc, int64_t M, int
     }
     double* yh = (dev && yhat_out) ? yhat_out + a : h->yhat.p;
     if ((rc = fp64_moments(h, xc, m, yh, eval_mse, &pt, &lc))) return rc;
+    const bool gen_trend = h->trend != B200BO_TREND_CONSTANT;
+    double* mt = nullptr;  // p > 1 trend: the finished MSE of this chunk
+    if (gen_trend) {
+      mt = eval_mse ? ((dev && mse_out) ? mse_out + a : h->mse.p) : nullptr;
+      if ((rc = trend_finish(h, xc, m, yh, mt, &lc))) return rc;
+    }
     if (eval_mse) {
       pt.begin(2);
       double* mo = mse_out ? (dev ? mse_out + a : h->mse.p) : nullptr;
       if (do_acq) {
         double* vp = vals ? (dev ? vals : h->vals.p) : nullptr;
-        if ((rc = acq_stage(h, yh, m, a, nullptr, acq_id, minimize, plugin, q, vp, dev ? M : Mc, dev ? a : 0, mo, &lc)))
+        if ((rc = acq_stage(h, yh, m, a, nullptr, acq_id, minimize, plugin, q, vp, dev ? M : Mc, dev ? a : 0, mo, &lc, mt)))
           return rc;
+      } else if (gen_trend) {
+        // trend_finish wrote the MSE already
       } else {
         AcqArgs g{};
         g.yhat = yh; g.sumsq = h->sumsq.p; g.dotf = h->dotf.p; g.mse_out = mo;
@@ -1402,7 +1562,8 @@ static int run_candidates(b200bo_handle h, const double* Xc, int64_t M, int loc,
   CHECK_ARG(loc == B200BO_HOST || loc == B200BO_DEVICE, "bad loc");
   CU_TRY(cudaSetDevice(h->device));
   // the tensor-core pass needs the variance (its product is rt) and cannot return all q x M values exactly
-  if (h->prec == B200BO_PREC_FAST && fast_supported(h) && eval_mse && !vals && M > 0 && q <= fk::BAND_MAX_Q) {
+  if (h->prec == B200BO_PREC_FAST && fast_supported(h) && h->trend == B200BO_TREND_CONSTANT && eval_mse && !vals && M > 0 &&
+      q <= fk::BAND_MAX_Q) {
     bool fell_back = false;
     int rc = run_candidates_fast(h, Xc, M, loc, eval_mse, yhat_out, mse_out, acq_id, minimize, plugin, params, q,
                                  best_val, best_idx, &fell_back);
@@ -1573,6 +1734,7 @@ static int grad_common(b200bo_handle h, const double* Xc, int64_t M, int acq_id,
   CHECK_ARG(h && (Xc || M == 0), "NULL argument");
   if (!h->factored) return set_err(B200BO_E_STATE, "gradient before a successful factor()");
   CHECK_ARG(h->corr != CUBIC, "the cubic kernel has no gradient (corr_dx: `pass`, gpr.py:654-655)");
+  CHECK_ARG(h->trend == B200BO_TREND_CONSTANT, "the posterior gradient is implemented for the constant trend");
   CU_TRY(cudaSetDevice(h->device));
   int rc;
   if ((rc = ensure_predict_ws(h, 1, false))) return rc;

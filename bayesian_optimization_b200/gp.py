@@ -30,6 +30,7 @@ _CORR_IDS = {
     "absolute_exponential": _lib.CORR_ABSEXP,
     "cubic": _lib.CORR_CUBIC,
 }
+_TREND_IDS = {"constant_trend": _lib.TREND_CONSTANT, "linear_trend": _lib.TREND_LINEAR, "quadratic_trend": _lib.TREND_QUADRATIC}
 _MODES = {"noiseless": _lib.MODE_NOISELESS, "noisy": _lib.MODE_NOISY, "noise_estim": _lib.MODE_NOISE_ESTIM}
 
 
@@ -156,8 +157,13 @@ class GaussianProcess:
             y = y.reshape(-1, 1)
         if y.shape[1] != 1:
             raise NotImplementedError("multi-target y is not implemented on device (SURVEY.md §8f rank 4)")
-        if not isinstance(self.mean, constant_trend) and type(self.mean).__name__ != "constant_trend":
-            raise NotImplementedError("only constant_trend has a device implementation (SURVEY.md §8f rank 4)")
+        tname = type(self.mean).__name__
+        if tname not in _TREND_IDS:
+            raise NotImplementedError("trend %s has no device implementation (constant, linear, quadratic do)" % tname)
+        self._trend_id = _TREND_IDS[tname]
+        self._p = int(self.mean.n_dim)
+        if self._p > 64:
+            raise NotImplementedError("at most 64 trend basis functions are supported on device")
         self.X, self.y = np.ascontiguousarray(X, dtype=np.float64), np.ascontiguousarray(y, dtype=np.float64)
         self._check_params()
         self._cache = {}
@@ -179,7 +185,7 @@ class GaussianProcess:
         theta, last = self._split_par(par)
         nv = float(np.atleast_1d(self.noise_var)[0]) if self.estimation_mode == "noisy" else 0.0
         llf, s2, nvo, status = self.engine.factor(self._corr_id, theta, _MODES[self.estimation_mode], last, nv,
-                                                  _lib.TREND_CONSTANT, self._beta_fixed())
+                                                  self._trend_id, self._beta_fixed())
         self._cache = {}
         return llf, s2, nvo, status
 
@@ -211,7 +217,7 @@ class GaussianProcess:
         fails (:842-847) or exp(llf) > 1 (:872-875).  ``env`` receives sigma2 / noise_var as upstream (:904-906)."""
         theta, s2, nv = self._split_par_restricted(par)
         n_par = np.size(par)
-        llf, status = self.engine.factor_restricted(self._corr_id, theta, s2, nv, _lib.TREND_CONSTANT, self._beta_fixed())
+        llf, status = self.engine.factor_restricted(self._corr_id, theta, s2, nv, self._trend_id, self._beta_fixed())
         self._cache = {}
         if status != _lib.FIT_OK:
             return (-np.inf, np.zeros((n_par, 1))) if eval_grad else -np.inf
@@ -225,7 +231,7 @@ class GaussianProcess:
     def _refactor(self):
         if getattr(self, "_restricted_par", None) is not None:
             _, status = self.engine.factor_restricted(self._corr_id, self.theta_, self._restricted_par[0],
-                                                      self._restricted_par[1], _lib.TREND_CONSTANT, self._beta_fixed())
+                                                      self._restricted_par[1], self._trend_id, self._beta_fixed())
             if status != _lib.FIT_OK:  # pragma: no cover - the same inputs factored before
                 raise RuntimeError("re-factorisation of a fitted model failed")
             return
@@ -284,7 +290,7 @@ class GaussianProcess:
                                 if self.likelihood == "restricted" else None)
         assert len(self.sigma2) == self.y.shape[1]
         if self.estimate_trend:
-            self.mean.beta = self.engine.state(_lib.STATE_BETA)  # gpr.py:787
+            self.mean.beta = self.engine.state(_lib.STATE_BETA, self._p)  # gpr.py:787
         self.is_fitted = True
 
     def fit(self, X, y):
@@ -342,15 +348,23 @@ class GaussianProcess:
 
     @property
     def Ft(self):
-        return self._state("Ft", _lib.STATE_FT, (-1, 1)) if self.estimate_trend else None
+        if not self.estimate_trend:
+            return None
+        if "Ft" not in self._cache:
+            self._cache["Ft"] = self.engine.state(_lib.STATE_FT, self._p).reshape(-1, self._p)
+        return self._cache["Ft"]
 
     @property
     def G(self):
-        return self._state("G", _lib.STATE_G, (1, 1)) if self.estimate_trend else None
+        if not self.estimate_trend:
+            return None
+        if "G" not in self._cache:
+            self._cache["G"] = self.engine.state(_lib.STATE_G, self._p).reshape(self._p, self._p)
+        return self._cache["G"]
 
     @property
     def Q(self):
-        return self.Ft / self.G[0, 0] if self.estimate_trend else None
+        return np.linalg.solve(self.G.T, self.Ft.T).T if self.estimate_trend else None  # Ft = Q G
 
     # ---- predict (gpr.py:424-535) ----------------------------------------------------------------------
     def predict(self, X, eval_MSE=False, batch_size=None):

@@ -3,7 +3,8 @@
 Reference: bayes_optim/surrogate/gaussian_process/trend.py.  ``constant_trend`` (:69-91) is what ``fmin``
 and every upstream GP test use (bayes_optim/__init__.py:148, unittest/test_BO.py:34); ``beta=None`` means
 the coefficient is estimated (ordinary kriging), a number means simple kriging (gpr.py:269-275).
-The device implements the constant trend; the basis value F(x) = 1 is a literal inside the kernels.
+The device evaluates the bases itself (constant: the literal 1 inside the kernels; linear / quadratic:
+csrc/trend_kernels.cuh); these classes carry the coefficients and answer the host-side questions (F, Jacobian).
 """
 from __future__ import annotations
 
@@ -68,3 +69,43 @@ class constant_trend(BasisExpansionTrend):
     def Hessian(self, x):
         self.check_input(x)
         return np.zeros((self.n_feature, self.n_feature, self.n_dim))
+
+
+class linear_trend(BasisExpansionTrend):
+    """trend.py:94-116: first-order polynomial, p = n + 1, f(x) = [1, x_1, ..., x_n]."""
+
+    def __init__(self, n_feature: int, beta=None):
+        super().__init__(n_feature, n_feature + 1, beta)
+
+    def F(self, X):
+        X = self.check_input(X)
+        return np.c_[np.ones(X.shape[0]), X]
+
+    def Jacobian(self, x):
+        x = self.check_input(x)
+        assert x.shape[0] == 1
+        return np.r_[np.zeros((1, self.n_feature)), np.eye(self.n_feature)]
+
+    def Hessian(self, x):
+        self.check_input(x)
+        return np.zeros((self.n_feature, self.n_feature, self.n_dim))
+
+
+class quadratic_trend(BasisExpansionTrend):
+    """trend.py:119-142: second-order polynomial, f(x) = [1, {x_i}, {x_k x_j, j >= k}], p = (n + 1)(n + 2) / 2."""
+
+    def __init__(self, n_feature: int, beta=None):
+        super().__init__(n_feature, (n_feature + 1) * (n_feature + 2) // 2, beta)
+
+    def F(self, X):
+        X = self.check_input(X)
+        f = np.c_[np.ones(X.shape[0]), X]
+        for k in range(self.n_feature):
+            f = np.c_[f, X[:, k, np.newaxis] * X[:, k:]]
+        return f
+
+    def Jacobian(self, X):
+        raise NotImplementedError  # trend.py:138-139
+
+    def Hessian(self, X):
+        raise NotImplementedError

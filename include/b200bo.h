@@ -45,7 +45,12 @@ typedef struct b200bo_ctx* b200bo_handle;
 #define B200BO_MODE_NOISE_ESTIM 2 /* R = a R0 + (1-a) I          par = [theta, a]     gpr.py:949-961 */
 
 /* trend ids: surrogate/gaussian_process/trend.py */
-#define B200BO_TREND_CONSTANT 0 /* constant_trend, p = 1   trend.py:69-91 */
+#define B200BO_TREND_CONSTANT 0  /* constant_trend, p = 1                                   trend.py:69-91  */
+#define B200BO_TREND_LINEAR 1    /* linear_trend, f = [1, x], p = D + 1                     trend.py:94-116 */
+#define B200BO_TREND_QUADRATIC 2 /* quadratic_trend, f = [1, x, {x_k x_j, j >= k}], p = (D+1)(D+2)/2  :119-142 */
+/* p <= 64.  p > 1 runs on the float64 path (B200BO_PREC_FAST falls back to it); beta_or_null then holds p values and
+ * B200BO_STATE_FT / _BETA / _G have N*p / p / p*p elements (row-major; G = the R factor of the thin QR of Ft with
+ * LAPACK's sign convention, gpr.py:805). */
 
 /* factor status (out_status of b200bo_factor) */
 #define B200BO_FIT_OK 0

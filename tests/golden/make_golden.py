@@ -33,7 +33,7 @@ CORR = {
 
 
 def make_gp(corr, D, mode, ok, nugget, beta=0.0, trend=go.TREND_CONSTANT):
-    tcls = {go.TREND_CONSTANT: ns.constant_trend, go.TREND_LINEAR: ns.linear_trend}[trend]
+    tcls = {go.TREND_CONSTANT: ns.constant_trend, go.TREND_LINEAR: ns.linear_trend, go.TREND_QUADRATIC: ns.quadratic_trend}[trend]
     mean = tcls(D) if ok else tcls(D, beta=beta)
     kw = dict(mean=mean, corr=CORR[corr], thetaL=[1e-5] * D, thetaU=[1e2] * D)
     if mode == go.MODE_NOISELESS:
@@ -331,9 +331,37 @@ def restricted():
     save("restricted.npz", cases)
 
 
+def trends():
+    """linear / quadratic regression trends (trend.py:94-142), ordinary (beta estimated) and simple (beta given)
+    kriging, the three estimation modes: fit state, predict, acquisition values."""
+    rng = np.random.default_rng(41)
+    N, D, M = 180, 3, 32
+    X = rng.uniform(-1, 1.5, (N, D))
+    y = X[:, 0] - 0.5 * X[:, 1] * X[:, 2] + np.sin(3 * X).sum(axis=1) + 0.2 * rng.standard_normal(N)
+    y = (y - y.mean()) / y.std()
+    Xc = rng.uniform(-1, 1.5, (M, D))
+    theta = np.array([0.8, 0.4, 1.3])
+    cases = {}
+    for trend, tn, p in [(go.TREND_LINEAR, "lin", D + 1), (go.TREND_QUADRATIC, "quad", (D + 1) * (D + 2) // 2)]:
+        for corr, cn in [(go.CORR_RBF, "rbf"), (go.CORR_MATERN52, "m52")]:
+            for mode, mn, last, nug in [(go.MODE_NOISELESS, "nl", None, None), (go.MODE_NOISY, "ny", 0.8, 1e-2),
+                                        (go.MODE_NOISE_ESTIM, "ne", 0.95, 1e-2)]:
+                if mode == go.MODE_NOISELESS and corr == go.CORR_RBF:
+                    continue  # ill-conditioned without a nugget
+                for ok in (True, False):
+                    name = f"{tn}_{cn}_{mn}_{'ok' if ok else 'sk'}"
+                    cases[name] = run_case(X, y, Xc, corr, theta, mode, ok, last, nug, trend=trend,
+                                           beta=np.linspace(-0.3, 0.4, p))
+                    print(name, cases[name]["llf"])
+    save("trends.npz", cases)
+
+
 if __name__ == "__main__":
     if "--fit-only" in sys.argv:
         fit_full()
+        sys.exit(0)
+    if "--trends-only" in sys.argv:
+        trends()
         sys.exit(0)
     if "--restricted-only" in sys.argv:
         restricted()
@@ -347,5 +375,6 @@ if __name__ == "__main__":
     fit_full()
     acq_grad()
     restricted()
+    trends()
     if "--big" in sys.argv:
         canonical(True)

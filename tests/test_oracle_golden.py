@@ -220,3 +220,14 @@ def test_restricted_likelihood(name):
         yh, ms = go.predict(gp, c["Xc"])
         np.testing.assert_allclose(yh.ravel(), c["yhat"], rtol=1e-9, atol=1e-10)
         np.testing.assert_allclose(ms.ravel(), c["mse"], rtol=1e-8, atol=1e-11)
+
+
+TRENDS = load_golden("trends")
+
+
+@pytest.mark.parametrize("name", sorted(TRENDS))
+def test_trends(name):
+    """linear / quadratic regression trends (trend.py:94-142) through fit state, predict and the acquisition values"""
+    c = TRENDS[name]
+    gp = oracle_fit(c)
+    check_case(c, gp, c["Xc"], rtol=1e-8 if "_nl_" in name else 1e-10)
