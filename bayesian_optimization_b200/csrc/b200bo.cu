@@ -360,7 +360,7 @@ int b200bo_set_train(b200bo_handle h, const double* X, const double* y, int N, i
   CU_TRY(h->Xt.reserve(xt.size()));
   CU_TRY(h->y.reserve(ld));
   CU_TRY(h->F.reserve(ld));
-  CU_TRY(h->theta.reserve(D));
+  CU_TRY(h->theta.reserve(D + 1));
   CU_TRY(cudaMemcpyAsync(h->Xt.p, xt.data(), xt.size() * 8, cudaMemcpyHostToDevice, h->stream));
   CU_TRY(cudaMemcpyAsync(h->y.p, yy.data(), ld * 8, cudaMemcpyHostToDevice, h->stream));
   CU_TRY(cudaMemcpyAsync(h->F.p, ff.data(), ld * 8, cudaMemcpyHostToDevice, h->stream));
@@ -375,11 +375,15 @@ static int factor_impl(b200bo_handle h, int corr, const double* theta, int n_the
                        double* out_sigma2, double* out_noise_var, int* out_status, bool restricted) {
   CHECK_ARG(h && theta, "NULL argument");
   CHECK_ARG(h->N > 0, "set_train first");
-  CHECK_ARG(corr >= 0 && corr <= 5, "unknown correlation id");
+  CHECK_ARG(corr >= 0 && corr <= 6, "unknown correlation id");
   CHECK_ARG(mode >= 0 && mode <= 2, "unknown estimation mode");
   CHECK_ARG(trend >= B200BO_TREND_CONSTANT && trend <= B200BO_TREND_QUADRATIC, "unknown trend id");
   CHECK_ARG(trend_p(trend, h->D) <= TR_PMAX, "at most 64 trend basis functions are supported");
   CHECK_ARG(!(restricted && trend != B200BO_TREND_CONSTANT), "the restricted likelihood is implemented for the constant trend");
+  if (corr == GENEXP) {
+    CHECK_ARG(n_theta == 2 || n_theta == h->D + 1, "Length of theta must be 2 or D + 1");  // kernel.py:367-370
+    --n_theta;  // the last entry is the exponent
+  }
   CHECK_ARG(n_theta == 1 || n_theta == h->D, "Length of theta must be 1 or D");
   CU_TRY(cudaSetDevice(h->device));
   const int N = h->N, D = h->D, ld = h->ld, nb = ld / NB;
@@ -401,13 +405,14 @@ static int factor_impl(b200bo_handle h, int corr, const double* theta, int n_the
   CU_TRY(h->part.reserve((size_t)gchunks * ld));
   if (h->keepR) CU_TRY(h->Rkeep.reserve(nn));
 
-  std::vector<double> th(D);
+  std::vector<double> th(D + 1, 0.0);
   for (int d = 0; d < D; ++d) th[d] = theta[n_theta == 1 ? 0 : d];
+  if (corr == GENEXP) th[D] = theta[n_theta];
   cudaStream_t st = h->stream;
   h->evs.reset();
   PhaseTimer pt{h};
   int launches = 0;
-  CU_TRY(cudaMemcpyAsync(h->theta.p, th.data(), D * 8, cudaMemcpyHostToDevice, st));
+  CU_TRY(cudaMemcpyAsync(h->theta.p, th.data(), (D + 1) * 8, cudaMemcpyHostToDevice, st));
   CU_TRY(cudaMemsetAsync(h->status.p, 0, sizeof(int), st));
   cudaEvent_t e0 = h->evs.get(), e1 = h->evs.get();
   CU_TRY(cudaEventRecord(e0, st));
@@ -1082,7 +1087,7 @@ static int make_f16_map(CUtensorMap* map, const __half* base, int inner, int row
   return 0;
 }
 
-static bool fast_supported(const b200bo_ctx* h) { return h->corr != CUBIC && h->D <= 64; }
+static bool fast_supported(const b200bo_ctx* h) { return h->corr != CUBIC && h->corr != GENEXP && h->D <= 64; }
 
 static int ensure_fast_state(b200bo_handle h) {
   if (h->fast_ready) return 0;
@@ -1733,7 +1738,7 @@ static int grad_common(b200bo_handle h, const double* Xc, int64_t M, int acq_id,
                        double* yhat, double* mse, double* y_dx, double* mse_dx, double* val, double* dx) {
   CHECK_ARG(h && (Xc || M == 0), "NULL argument");
   if (!h->factored) return set_err(B200BO_E_STATE, "gradient before a successful factor()");
-  CHECK_ARG(h->corr != CUBIC, "the cubic kernel has no gradient (corr_dx: `pass`, gpr.py:654-655)");
+  CHECK_ARG(h->corr != CUBIC && h->corr != GENEXP, "this kernel has no gradient (corr_dx: `pass`, gpr.py:652-655)");
   CHECK_ARG(h->trend == B200BO_TREND_CONSTANT, "the posterior gradient is implemented for the constant trend");
   CU_TRY(cudaSetDevice(h->device));
   int rc;

@@ -51,6 +51,7 @@ __global__ void __launch_bounds__(256) kmat_assemble_kernel(AssembleArgs p) {
     xj[e] = p.Xt[(size_t)d * p.ld + j0 + c];
   }
   for (int d = tid; d < p.D; d += 256) th[d] = p.theta[d];
+  const double pw = p.corr == GENEXP ? p.theta[p.D] : 0.0;  // generalized_exponential: the exponent follows theta
   __syncthreads();
   // thread -> 4 rows x 4 cols (cols interleaved by 16 so smem reads of xj are conflict-free)
   const int tr = (tid / 16) * 4, tc = tid % 16;
@@ -69,7 +70,7 @@ __global__ void __launch_bounds__(256) kmat_assemble_kernel(AssembleArgs p) {
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
-      for (int b = 0; b < 4; ++b) acc[a][b] = corr_accum(p.corr, acc[a][b], thd, xa[a] - xb[b]);
+      for (int b = 0; b < 4; ++b) acc[a][b] = corr_accum_p(p.corr, acc[a][b], thd, xa[a] - xb[b], pw);
   }
   const double s2t = p.sigma2 + p.noise_var;
 #pragma unroll

@@ -13,7 +13,7 @@
 
 namespace b2 {
 
-enum Corr { RBF = 0, MATERN12 = 1, MATERN32 = 2, MATERN52 = 3, ABSEXP = 4, CUBIC = 5 };
+enum Corr { RBF = 0, MATERN12 = 1, MATERN32 = 2, MATERN52 = 3, ABSEXP = 4, CUBIC = 5, GENEXP = 6 };
 enum Acq { ACQ_EI = 0, ACQ_PI = 1, ACQ_UCB = 2, ACQ_MGFI = 3 };
 
 // ---- correlation: accumulate over features, then finish -------------------------------------------
@@ -30,10 +30,17 @@ B2_HD double corr_accum(int corr, double acc, double theta, double diff) {
   return acc + theta * (diff * diff);  // kernel.py:326-329 (RBF), :184-187 (Matern): sum theta_j d_j^2
 }
 
+// generalized_exponential carries its exponent next to theta: exp(-sum theta_j |d_j|^pw)   kernel.py:372-373
+B2_HD double corr_accum_p(int corr, double acc, double theta, double diff, double pw) {
+  if (corr == GENEXP) return acc + theta * pow(fabs(diff), pw);
+  return corr_accum(corr, acc, theta, diff);
+}
+
 B2_HD double corr_finish(int corr, double acc) {
   switch (corr) {
     case RBF:
     case ABSEXP:
+    case GENEXP:
       return exp(-acc);
     case MATERN12:
       return exp(-sqrt(acc));  // kernel.py:189-190

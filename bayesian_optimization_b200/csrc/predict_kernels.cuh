@@ -40,6 +40,7 @@ __global__ void __launch_bounds__(256) kstar_kernel(KstarArgs p) {
     xc[e] = (m0 + r < p.M) ? p.Xc[(size_t)(m0 + r) * p.D + d] : 0.0;
   }
   for (int d = tid; d < p.D; d += 256) th[d] = p.theta[d];
+  const double pw = p.corr == GENEXP ? p.theta[p.D] : 0.0;  // generalized_exponential: the exponent follows theta
   __syncthreads();
   double ysum[KS_ROWS];
 #pragma unroll
@@ -53,7 +54,7 @@ __global__ void __launch_bounds__(256) kstar_kernel(KstarArgs p) {
         double xd = p.Xt[(size_t)d * p.ld + n];
         double thd = th[d];
 #pragma unroll
-        for (int r = 0; r < KS_ROWS; ++r) acc[r] = corr_accum(p.corr, acc[r], thd, xc[r * p.D + d] - xd);
+        for (int r = 0; r < KS_ROWS; ++r) acc[r] = corr_accum_p(p.corr, acc[r], thd, xc[r * p.D + d] - xd, pw);
       }
     }
     double g = p.gamma[n];

@@ -29,6 +29,7 @@ _CORR_IDS = {
     "matern52": _lib.CORR_MATERN52,
     "absolute_exponential": _lib.CORR_ABSEXP,
     "cubic": _lib.CORR_CUBIC,
+    "generalized_exponential": _lib.CORR_GENEXP,  # theta carries the exponent as its last entry (kernel.py:367-373)
 }
 _TREND_IDS = {"constant_trend": _lib.TREND_CONSTANT, "linear_trend": _lib.TREND_LINEAR, "quadratic_trend": _lib.TREND_QUADRATIC}
 _MODES = {"noiseless": _lib.MODE_NOISELESS, "noisy": _lib.MODE_NOISY, "noise_estim": _lib.MODE_NOISE_ESTIM}

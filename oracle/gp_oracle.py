@@ -31,6 +31,7 @@ CORR_MATERN32 = 2  # matern(nu=1.5) = the string "matern"   kernel.py:192-195, g
 CORR_MATERN52 = 3  # matern(nu=2.5)       kernel.py:197-200
 CORR_ABSEXP = 4  # "absolute_exponential" kernel.py:247-286
 CORR_CUBIC = 5  # "cubic"                  kernel.py:419-466
+CORR_GENEXP = 6  # "generalized_exponential" kernel.py:332-374 (theta = [theta_1..n | theta, p])
 
 CORR_NAMES = {
     "squared_exponential": CORR_RBF,
@@ -75,6 +76,11 @@ def corr_values(corr: int, theta: np.ndarray, d: np.ndarray) -> np.ndarray:
     theta = np.asarray(theta, dtype=np.float64).ravel()
     d = np.asarray(d, dtype=np.float64)
     nf = d.shape[1]
+    if corr == CORR_GENEXP:  # kernel.py:362-374: theta = [theta | theta_1..n, p]
+        if theta.size not in (2, nf + 1):
+            raise ValueError("Length of theta must be 2 or %s" % (nf + 1))
+        th = np.repeat(theta[0], nf) if theta.size == 2 and nf > 1 else theta[:-1]
+        return np.exp(-np.sum(th.reshape(1, nf) * np.abs(d) ** theta[-1], axis=1))
     if theta.size not in (1, nf):
         raise ValueError("Length of theta must be 1 or %s" % nf)
     if corr == CORR_RBF:

@@ -29,13 +29,15 @@ CORR = {
     go.CORR_MATERN12: functools.partial(ns.matern, nu=0.5),
     go.CORR_ABSEXP: "absolute_exponential",
     go.CORR_CUBIC: "cubic",
+    go.CORR_GENEXP: "generalized_exponential",
 }
 
 
 def make_gp(corr, D, mode, ok, nugget, beta=0.0, trend=go.TREND_CONSTANT):
     tcls = {go.TREND_CONSTANT: ns.constant_trend, go.TREND_LINEAR: ns.linear_trend, go.TREND_QUADRATIC: ns.quadratic_trend}[trend]
     mean = tcls(D) if ok else tcls(D, beta=beta)
-    kw = dict(mean=mean, corr=CORR[corr], thetaL=[1e-5] * D, thetaU=[1e2] * D)
+    nt = D + 1 if corr == go.CORR_GENEXP else D
+    kw = dict(mean=mean, corr=CORR[corr], thetaL=[1e-5] * nt, thetaU=[1e2] * nt)
     if mode == go.MODE_NOISELESS:
         kw.update(nugget=None)
     elif mode == go.MODE_NOISY:
@@ -356,9 +358,36 @@ def trends():
     save("trends.npz", cases)
 
 
+def genexp():
+    """generalized_exponential (kernel.py:332-374): theta carries the exponent as its last entry; anisotropic and
+    isotropic theta, ordinary / simple kriging, the three estimation modes."""
+    rng = np.random.default_rng(51)
+    N, D, M = 140, 3, 24
+    X = rng.uniform(0, 2, (N, D))
+    y = np.cos(2 * X).sum(axis=1) + 0.2 * rng.standard_normal(N)
+    y = (y - y.mean()) / y.std()
+    Xc = rng.uniform(0, 2, (M, D))
+    Xc[:2] = X[:2]
+    cases = {}
+    # (the isotropic form theta = [theta, p] raises IndexError upstream, kernel.py:365-376: hstack leaves theta 1-D)
+    for tn, theta in [("ard", [0.6, 1.1, 0.3, 1.6]), ("p2", [0.5, 0.9, 0.4, 2.0])]:
+        for mode, mn, last, nug in [(go.MODE_NOISELESS, "nl", None, None), (go.MODE_NOISY, "ny", 0.8, 1e-2),
+                                    (go.MODE_NOISE_ESTIM, "ne", 0.95, 1e-2)]:
+            if mode == go.MODE_NOISELESS and tn == "p2":
+                continue
+            for ok in (True, False):
+                name = f"gexp_{tn}_{mn}_{'ok' if ok else 'sk'}"
+                cases[name] = run_case(X, y, Xc, go.CORR_GENEXP, theta, mode, ok, last, nug, beta=0.1)
+                print(name, cases[name]["llf"])
+    save("genexp.npz", cases)
+
+
 if __name__ == "__main__":
     if "--fit-only" in sys.argv:
         fit_full()
+        sys.exit(0)
+    if "--genexp-only" in sys.argv:
+        genexp()
         sys.exit(0)
     if "--trends-only" in sys.argv:
         trends()
@@ -376,5 +405,6 @@ if __name__ == "__main__":
     acq_grad()
     restricted()
     trends()
+    genexp()
     if "--big" in sys.argv:
         canonical(True)

@@ -18,6 +18,7 @@ CORR_ARG = {
     go.CORR_MATERN12: functools.partial(matern, nu=0.5),
     go.CORR_ABSEXP: "absolute_exponential",
     go.CORR_CUBIC: "cubic",
+    go.CORR_GENEXP: "generalized_exponential",
 }
 
 
@@ -25,7 +26,8 @@ def device_gp(c, D, beta=None):
     """GaussianProcess configured like tests/golden/make_golden.py:make_gp"""
     mode, ok = int(c["mode"]), bool(c["ok"])
     mean = b2.constant_trend(D) if ok else b2.constant_trend(D, beta=float(np.ravel(c["beta_in"])[0]) if beta is None else beta)
-    kw = dict(mean=mean, corr=CORR_ARG[int(c["corr"])], thetaL=[1e-5] * D, thetaU=[1e2] * D)
+    nt = D + 1 if int(c["corr"]) == go.CORR_GENEXP else D  # generalized_exponential: theta carries the exponent
+    kw = dict(mean=mean, corr=CORR_ARG[int(c["corr"])], thetaL=[1e-5] * nt, thetaU=[1e2] * nt)
     if mode == go.MODE_NOISELESS:
         kw.update(nugget=None)
     elif mode == go.MODE_NOISY:

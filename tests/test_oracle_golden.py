@@ -231,3 +231,14 @@ def test_trends(name):
     c = TRENDS[name]
     gp = oracle_fit(c)
     check_case(c, gp, c["Xc"], rtol=1e-8 if "_nl_" in name else 1e-10)
+
+
+GENEXP = load_golden("genexp")
+
+
+@pytest.mark.parametrize("name", sorted(GENEXP))
+def test_generalized_exponential(name):
+    """generalized_exponential (kernel.py:332-374), theta = [theta_1..n, p]"""
+    c = GENEXP[name]
+    gp = oracle_fit(c)
+    check_case(c, gp, c["Xc"], rtol=1e-7 if "_nl_" in name else 1e-10)
