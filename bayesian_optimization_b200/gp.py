@@ -108,10 +108,13 @@ class GaussianProcess:
         self.precision = precision
         self._engine: Optional[Engine] = None
         self._cache = {}
+        self._sub = None  # multi-target y (N, k > 1): one single-target model per column (same R, own Yt / rho / gamma)
 
     # ---- engine plumbing ---------------------------------------------------------------------------
     @property
     def engine(self) -> Engine:
+        if getattr(self, "_sub", None):
+            return self._sub[0].engine
         if self._engine is None:
             self._engine = Engine(self.device)  # raises without libb200bo.so / a B200
             self._engine.set_precision(_lib.PREC_FAST if getattr(self, "precision", "fp64") == "fast" else _lib.PREC_FP64)
@@ -157,7 +160,8 @@ class GaussianProcess:
         if len(y.shape) == 1:
             y = y.reshape(-1, 1)
         if y.shape[1] != 1:
-            raise NotImplementedError("multi-target y is not implemented on device (SURVEY.md §8f rank 4)")
+            return self._check_data_multi(X, y)
+        self._sub = None
         tname = type(self.mean).__name__
         if tname not in _TREND_IDS:
             raise NotImplementedError("trend %s has no device implementation (constant, linear, quadratic do)" % tname)
@@ -171,6 +175,53 @@ class GaussianProcess:
         self.engine.set_train(self.X, self.y[:, 0])
         if self.estimate_trend:
             self.F = self.mean.F(self.X)
+
+    # ---- multi-target y (N, k): gpr.py keeps Yt, rho, gamma, beta, sigma2 per column over ONE factorisation ---------
+    # (:799 Yt = L^-1 y, :806-808 rho, :934-979 sigma2 (k,), likelihood vector summed at :1040, predict :490, :502-505).
+    # Here every column gets its own single-target model / device handle; each repeats the deterministic factorisation
+    # (k is the number of objectives: 2-3), so the per-column states are exactly those of the reference.
+    def _check_data_multi(self, X, y):
+        import copy
+
+        self.X, self.y = np.ascontiguousarray(X, dtype=np.float64), np.ascontiguousarray(y, dtype=np.float64)
+        self._check_params()
+        self._cache = {}
+        if self.estimate_trend:
+            self.F = self.mean.F(self.X)
+        if self._sub is None or len(self._sub) != y.shape[1]:
+            self._sub = []
+            for _ in range(y.shape[1]):
+                g = GaussianProcess(mean=copy.deepcopy(self.mean), corr=self.corr, theta0=self.theta0, thetaL=self.thetaL,
+                                    thetaU=self.thetaU, nugget=self.nugget, noise_estim=self.noise_estim,
+                                    optimizer=self.optimizer, likelihood=self.likelihood, device=self.device,
+                                    precision=self.precision)
+                self._sub.append(g)
+        for t, g in enumerate(self._sub):
+            g._check_data(self.X, self.y[:, t])
+
+    def _sync_sub(self):
+        for g in self._sub:
+            g.estimation_mode, g.noise_var = self.estimation_mode, self.noise_var
+
+    def _llf_multi(self, par, env, eval_grad):
+        self._sync_sub()
+        n_par = np.size(par)
+        envs = [{} for _ in self._sub]
+        outs = [g.log_likelihood_concentrated(par, e, eval_grad) for g, e in zip(self._sub, envs)]
+        llfs = [o[0] if eval_grad else o for o in outs]
+        self._cache = {}
+        if not np.all(np.isfinite(llfs)):  # any(log_likelihood > 0) or a failed factorisation: gpr.py:981-982
+            return (-np.inf, np.zeros((n_par, 1))) if eval_grad else -np.inf
+        if env is not None:
+            env["sigma2"] = np.array([np.atleast_1d(e["sigma2"])[0] for e in envs])
+            nv = np.array([np.atleast_1d(e["noise_var"])[0] for e in envs])
+            env["noise_var"] = nv if self.estimation_mode == "noise_estim" else envs[0]["noise_var"]
+        llf = float(np.sum(llfs))  # gpr.py:1040
+        if eval_grad:
+            # sum of the per-target gradients (upstream's k > 1 formula mixes gamma gamma^T of ALL targets with every
+            # sigma2_t, gpr.py:997-1010; the optimum it steers to is the same stationary point of the summed likelihood)
+            return llf, np.sum([np.asarray(o[1], dtype=np.float64).reshape(-1, 1) for o in outs], axis=0)
+        return llf
 
     # ---- likelihood at given hyper-parameters (gpr.py:920-991) -----------------------------------------
     def _split_par(self, par):
@@ -193,6 +244,8 @@ class GaussianProcess:
     def log_likelihood_concentrated(self, par, env=None, eval_grad=False):
         """Concentrated log-likelihood at ``par`` on the device; -inf when the factorisation fails or the
         value is positive (gpr.py:981-982).  ``env`` receives sigma2 / noise_var like the reference's."""
+        if self._sub:
+            return self._llf_multi(par, env, eval_grad)
         llf, s2, nvo, status = self._factor(par)
         n_par = np.size(par)
         if status != _lib.FIT_OK:
@@ -216,6 +269,8 @@ class GaussianProcess:
     def log_likelihood_restricted(self, par, env=None, eval_grad=False):
         """Restricted (REML) log-likelihood at ``par`` on the device (gpr.py:813-918); -inf when the factorisation
         fails (:842-847) or exp(llf) > 1 (:872-875).  ``env`` receives sigma2 / noise_var as upstream (:904-906)."""
+        if self._sub:
+            raise NotImplementedError("the restricted likelihood is implemented for one target")
         theta, s2, nv = self._split_par_restricted(par)
         n_par = np.size(par)
         llf, status = self.engine.factor_restricted(self._corr_id, theta, s2, nv, self._trend_id, self._beta_fixed())
@@ -290,6 +345,14 @@ class GaussianProcess:
         self._restricted_par = ((float(self.sigma2[0]), float(np.atleast_1d(self.noise_var)[0]))
                                 if self.likelihood == "restricted" else None)
         assert len(self.sigma2) == self.y.shape[1]
+        if self._sub:
+            for t, g in enumerate(self._sub):
+                e = {"sigma2": np.atleast_1d(self.sigma2[t]), "noise_var": np.atleast_1d(np.atleast_1d(self.noise_var)[t if np.size(self.noise_var) > 1 else 0])}
+                g._adopt(theta, par_last, e)
+            if self.estimate_trend:
+                self.mean.beta = np.hstack([np.asarray(g.mean.beta).reshape(-1, 1) for g in self._sub])  # (p, k)
+            self.is_fitted = True
+            return
         if self.estimate_trend:
             self.mean.beta = self.engine.state(_lib.STATE_BETA, self._p)  # gpr.py:787
         self.is_fitted = True
@@ -326,6 +389,11 @@ class GaussianProcess:
 
     # ---- lazily fetched state ------------------------------------------------------------------------
     def _state(self, key, what, shape=None):
+        if self._sub and key not in self._cache:
+            if key == "C":  # one factorisation for all targets
+                self._cache[key] = self._sub[0]._state(key, what, shape)
+            else:           # gamma, Yt, rho: one column per target
+                self._cache[key] = np.hstack([g._state(key, what, (-1, 1)) for g in self._sub])
         if key not in self._cache:
             a = self.engine.state(what)
             self._cache[key] = a if shape is None else a.reshape(shape)
@@ -351,6 +419,8 @@ class GaussianProcess:
     def Ft(self):
         if not self.estimate_trend:
             return None
+        if self._sub:
+            return self._sub[0].Ft
         if "Ft" not in self._cache:
             self._cache["Ft"] = self.engine.state(_lib.STATE_FT, self._p).reshape(-1, self._p)
         return self._cache["Ft"]
@@ -359,6 +429,8 @@ class GaussianProcess:
     def G(self):
         if not self.estimate_trend:
             return None
+        if self._sub:
+            return self._sub[0].G
         if "G" not in self._cache:
             self._cache["G"] = self.engine.state(_lib.STATE_G, self._p).reshape(self._p, self._p)
         return self._cache["G"]
@@ -382,6 +454,11 @@ class GaussianProcess:
             raise Exception("batch_size must be a positive integer")
         # batch_size only bounds host memory in the reference (and its branch is dead on Python 3,
         # gpr.py:520); the engine streams candidates in SM-count-sized chunks regardless.
+        if self._sub:  # (M, k) columns; the MSE factor is shared, sigma2 is per target (gpr.py:502-505)
+            outs = [g.predict(X, eval_MSE=eval_MSE) for g in self._sub]
+            if eval_MSE:
+                return np.hstack([o[0] for o in outs]), np.hstack([o[1] for o in outs])
+            return np.hstack(outs)
         yhat, mse = self.engine.predict(X, eval_mse=bool(eval_MSE))
         if eval_MSE:
             return yhat.reshape(-1, 1), mse.reshape(-1, 1)
@@ -391,6 +468,8 @@ class GaussianProcess:
     # ---- posterior gradient (gpr.py:537-576) --------------------------------------------------------------
     def gradient(self, x):
         """d yhat / dx and d MSE / dx at ONE point: ((D, 1), (D, 1)) exactly as the reference returns them."""
+        if self._sub:
+            raise NotImplementedError("gradient is implemented for one target")
         x = np.atleast_2d(np.asarray(x, dtype=np.float64))
         n_eval, nf = x.shape
         if nf != self.X.shape[1]:

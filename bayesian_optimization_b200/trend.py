@@ -29,7 +29,14 @@ class BasisExpansionTrend:
         if beta is not None:
             if not hasattr(beta, "__iter__"):
                 beta = np.array([beta] * self.n_dim)
-            beta = np.atleast_2d(beta).reshape(-1, 1)
+            b2d = np.atleast_2d(beta)
+            if b2d.ndim == 2 and b2d.shape[0] == self.n_dim and b2d.shape[1] > 1 and self.n_dim > 1 or (
+                    self.n_dim == 1 and np.ndim(beta) == 2 and np.shape(beta)[0] == 1 and np.shape(beta)[1] > 1):
+                # (p, k): one coefficient column per target of a multi-target fit with beta estimated -- upstream
+                # flattens this and raises (trend.py:25-28), which is why its ordinary kriging cannot take y (N, k > 1)
+                self._beta = np.asarray(b2d, dtype=np.float64)
+                return
+            beta = b2d.reshape(-1, 1)
             if len(beta) != self.n_dim:
                 raise Exception("Shapes of beta and F do not match.")
         self._beta = beta

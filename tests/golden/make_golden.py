@@ -382,9 +382,44 @@ def genexp():
     save("genexp.npz", cases)
 
 
+def multi_target():
+    """y (N, 2): per-target Yt / rho / gamma / beta / sigma2 over one factorisation (gpr.py:799-808, :934-979), the
+    summed likelihood (:1040) and (M, 2) predictions (:490, :502-505)."""
+    rng = np.random.default_rng(61)
+    N, D, M = 130, 3, 20
+    X = rng.uniform(0, 2, (N, D))
+    Y = np.c_[np.sin(2 * X).sum(axis=1), np.cos(3 * X[:, 0]) - X[:, 1] * X[:, 2]] + 0.2 * rng.standard_normal((N, 2))
+    Y = (Y - Y.mean(axis=0)) / Y.std(axis=0)
+    Xc = rng.uniform(0, 2, (M, D))
+    theta = [0.7, 0.4, 1.2]
+    cases = {}
+    for corr, cn in [(go.CORR_RBF, "rbf"), (go.CORR_MATERN32, "m32")]:
+        for mode, mn, last, nug in [(go.MODE_NOISELESS, "nl", None, None), (go.MODE_NOISY, "ny", 0.8, 1e-2),
+                                    (go.MODE_NOISE_ESTIM, "ne", 0.95, 1e-2)]:
+            if mode == go.MODE_NOISELESS and corr == go.CORR_RBF:
+                continue
+            for ok in (False,):  # ordinary kriging with k > 1 raises upstream: the beta setter flattens (p, k) (trend.py:25-28)
+                gp = make_gp(corr, D, mode, ok, nug, 0.1)
+                llf = ref_loader.fixed_theta_fit(gp, X, Y, theta, last)
+                gp.sigma2 = np.atleast_1d(gp.sigma2)
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    yh, ms = gp.predict(Xc, eval_MSE=True)
+                name = f"mt_{cn}_{mn}_{'ok' if ok else 'sk'}"
+                cases[name] = dict(X=X, y=Y, Xc=Xc, corr=corr, theta=np.asarray(theta, float), mode=mode, ok=ok,
+                                   par_last=np.nan if last is None else last, nugget=0.0 if nug is None else nug, beta_in=0.1,
+                                   llf=llf, sigma2=np.ravel(gp.sigma2), noise_var=np.ravel(gp.noise_var),
+                                   beta=np.asarray(gp.mean.beta, float), gamma=gp.gamma, yhat=yh, mse=ms)
+                print(name, llf, np.ravel(gp.sigma2))
+    save("multi_target.npz", cases)
+
+
 if __name__ == "__main__":
     if "--fit-only" in sys.argv:
         fit_full()
+        sys.exit(0)
+    if "--multi-only" in sys.argv:
+        multi_target()
         sys.exit(0)
     if "--genexp-only" in sys.argv:
         genexp()
@@ -406,5 +441,6 @@ if __name__ == "__main__":
     restricted()
     trends()
     genexp()
+    multi_target()
     if "--big" in sys.argv:
         canonical(True)
