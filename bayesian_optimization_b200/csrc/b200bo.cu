@@ -1243,7 +1243,6 @@ static int launch_fused(b200bo_handle h, const double* xc_dev, long long m, size
       fk4::ReplayArgs ra;
       ra.scratch = h->r_scratch.p;
       ra.n_store = h->ld / fk::KC;
-      ra.debug = getenv("B200BO_DEBUG_BITS") ? atoi(getenv("B200BO_DEBUG_BITS")) : 0;  // timing experiments (wrong results)
       h->last_n_store = ra.n_store;
       switch (h->corr) {
         case RBF: FK5_LAUNCH(RBF); break;
@@ -1254,7 +1253,6 @@ static int launch_fused(b200bo_handle h, const double* xc_dev, long long m, size
     } else if (h->use_pair && h->use_replay) {
       fk4::ReplayArgs ra;
       ra.scratch = h->r_scratch.p;
-      ra.debug = 0;
       const size_t blk = (size_t)fk::BM * fk::KC;
       const int planes = nprod == 1 ? 1 : 2;
       ra.n_store = (int)std::min<size_t>((size_t)(h->ld / fk::KC), h->r_scratch.n / ((size_t)h->num_sms * planes * blk)) & ~1;

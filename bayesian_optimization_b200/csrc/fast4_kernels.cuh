@@ -34,8 +34,6 @@ struct ReplayMaps {
 struct ReplayArgs {
   __half* scratch;  // (gridDim.x, n_store, planes, 128 rows, 64) fp16, row-major; planes = 1 (one product) or 2 (hi, lo)
   int n_store;      // chunks of a tile kept in the scratch (even; 0 = recompute everything, i.e. generation 3)
-  int debug;        // generation 5, developer timing experiments only (results are WRONG when set): bit 0 producers skip the
-                    // Gram tcgen05.ld, bit 1 no Gram MMAs, bit 2 no correlation math, bit 3 no scratch stores
 };
 
 

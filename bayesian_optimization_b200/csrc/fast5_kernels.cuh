@@ -300,7 +300,7 @@ predict_fused_decoupled_kernel(const __grid_constant__ fk4::ReplayMaps rmaps, co
           const uint64_t dx_lo = umma_desc_sw128(sbase + OFF_X + x * X_STAGE_BYTES + XH_PLANE);
           const uint32_t tg = tmem_base + (uint32_t)(G_COL0 + KC * (i & 1));
           if (el) {
-            for (int ks = 0; ks < ((ra.debug & 2) ? 0 : p.dk_steps); ++ks) {
+            for (int ks = 0; ks < p.dk_steps; ++ks) {
               const uint64_t o = (uint64_t)(ks * 2);
               umma_f16_pair(tg, dax_hi + o, dx_hi + o, idesc_gram, ks != 0);
               umma_f16_pair(tg, dax_hi + o, dx_lo + o, idesc_gram, 1);
@@ -528,14 +528,9 @@ predict_fused_decoupled_kernel(const __grid_constant__ fk4::ReplayMaps rmaps, co
         // read the whole Gram row segment first and hand the TMEM block back: the Gram MMA of chunk j + 2 then
         // runs while this group is still computing
         uint32_t gr0[16], gr1[16];
-        if (!(ra.debug & 1)) {
-          fk2::tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(G_COL0 + KC * grp + 32 * ch), gr0);
-          fk2::tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(G_COL0 + KC * grp + 32 * ch + 16), gr1);
-          tmem_ld_wait();
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) gr0[i] = gr1[i] = (uint32_t)(lane + i);
-        }
+        fk2::tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(G_COL0 + KC * grp + 32 * ch), gr0);
+        fk2::tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(G_COL0 + KC * grp + 32 * ch + 16), gr1);
+        tmem_ld_wait();
         tc_fence_before();
         // the scratch slot of this chunk is free once the previous tile's last replay of it has been consumed
         if (elected && tl > 0) spin_until_ge(cons_cnt, tl * (uint32_t)upt - (uint32_t)nch + (uint32_t)kc + 1u, p.err, 15);
@@ -557,7 +552,7 @@ predict_fused_decoupled_kernel(const __grid_constant__ fk4::ReplayMaps rmaps, co
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const float acc = fmaxf(fmaf(CG, __uint_as_float(gr[i]), am + bj[i]), 0.f);
-            kv[i] = (ra.debug & 4) ? acc : corr_from_acc<CORR>(acc);
+            kv[i] = corr_from_acc<CORR>(acc);
           }
 #pragma unroll
           for (int i = 0; i < 16; i += 4) {
@@ -581,15 +576,13 @@ predict_fused_decoupled_kernel(const __grid_constant__ fk4::ReplayMaps rmaps, co
               }
             }
             const uint32_t goff = (uint32_t)(((col0 >> 3) + c) * 16);  // plain row-major: the TMA load applies the swizzle
-            if (!(ra.debug & 8)) {
-              *(uint4*)(g_hi + goff) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-              if (NPROD == 3) *(uint4*)(g_lo + goff) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-            }
+            *(uint4*)(g_hi + goff) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            if (NPROD == 3) *(uint4*)(g_lo + goff) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           }
         }
         ysum_d += (double)ysum;
         fsum_d += (double)fsum;
-        if (!(ra.debug & 16)) asm volatile("fence.proxy.async.global;" ::: "memory");  // scratch stores -> visible to the TMA loads
+        asm volatile("fence.proxy.async.global;" ::: "memory");  // scratch stores -> visible to the TMA loads
         if (tr) p.trace[j * 8 + 6] = clock64();
         if (grp == 0) asm volatile("bar.sync 1, %0;" ::"n"(32 * NPW / 2) : "memory");
         else asm volatile("bar.sync 2, %0;" ::"n"(32 * NPW / 2) : "memory");

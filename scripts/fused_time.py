@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Kernel-only timing of the fused tensor-core kernel on a bench workload (developer tool; B200BO_DEBUG_BITS etc. apply).
+"""Kernel-only timing of the fused tensor-core kernel on a bench workload (developer tool; B200BO_FAST_KERNEL / B200BO_REPLAY_MB apply).
 usage: python scripts/fused_time.py [workload] [M] [products] [reps]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -18,6 +18,6 @@ gp = b2.GaussianProcess(mean=b2.constant_trend(D), corr=cfg.corr, thetaL=[1e-5] 
 gp.fit_fixed(X, y, theta, 1.0)
 Xc = workloads.canonical_candidates(M, D)
 ms = gp.engine.debug_fused_time(Xc, prod, reps)
-print("workload=%s N=%d D=%d M=%d products=%d bits=%s gen=%s: %.3f ms  %.2f Mcand/s  %.0f algorithmic TFLOP/s" % (
-    wl, N, D, M, prod, os.environ.get("B200BO_DEBUG_BITS", "0"), os.environ.get("B200BO_FAST_KERNEL", "default"),
+print("workload=%s N=%d D=%d M=%d products=%d gen=%s: %.3f ms  %.2f Mcand/s  %.0f algorithmic TFLOP/s" % (
+    wl, N, D, M, prod, os.environ.get("B200BO_FAST_KERNEL", "default"),
     ms, M / ms / 1e3, M * float(N) * N / ms / 1e9))
