@@ -70,6 +70,21 @@ struct DevBuf {
   }
 };
 
+// A replayable stretch of the factorisation (its kernels take pointers only): run eagerly the first time a
+// configuration is seen, captured into a CUDA graph the second time, replayed from then on.  The L-BFGS loop calls
+// factor() hundreds of times with the same shapes; the graph removes ~200 launches' worth of CPU time and most of the
+// inter-kernel gaps of the latency-bound panel chain.
+struct GraphSlot {
+  cudaGraphExec_t exec = nullptr;
+  const void* key[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int seen = 0, launches = 0;
+  void drop() {
+    if (exec) cudaGraphExecDestroy(exec);
+    exec = nullptr;
+    seen = 0;
+  }
+};
+
 struct EvPool {
   std::vector<cudaEvent_t> ev;
   size_t used = 0;
@@ -154,6 +169,12 @@ struct b200bo_ctx {
   int fast_kernel_pref = 5;   // 5: CTA pairs, producers decoupled through the scratch; 4: CTA pairs + r replay; 3: CTA pairs; 2: single-CTA Gram kernel; 1: first generation
   bool use_decoupled = false;
   cudaStream_t copy_stream = nullptr;
+  cudaStream_t la_stream = nullptr;  // low-priority helper stream of the Cholesky look-ahead
+  cudaStream_t inv_stream = nullptr; // diagonal-block inverses, off the critical path
+  std::vector<cudaEvent_t> la_ev;    // 3 events per panel (untimed)
+  int lookahead = 1;
+  int use_graphs = 1;
+  GraphSlot g_chol, g_trtri;
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_used[2] = {nullptr, nullptr};
   bool want_dbg_w = false;
   EvPool evs;
@@ -164,7 +185,7 @@ struct b200bo_ctx {
 namespace {
 
 template <typename Core, bool A_KM, bool B_KN>
-cudaError_t launch_gemm(b200bo_ctx* h, const GemmArgs& g, int M, int N, int batch) {
+cudaError_t launch_gemm_on(b200bo_ctx* h, cudaStream_t st, const GemmArgs& g, int M, int N, int batch) {
   auto kern = dgemm_kernel<64, 64, 32, 32, A_KM, B_KN, 3>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -173,8 +194,73 @@ cudaError_t launch_gemm(b200bo_ctx* h, const GemmArgs& g, int M, int N, int batc
     attr_set = true;
   }
   dim3 grid(N / 64, M / 64, batch);
-  kern<<<grid, Core::NT, Core::SMEM_BYTES, h->stream>>>(g);
+  kern<<<grid, Core::NT, Core::SMEM_BYTES, st>>>(g);
   return cudaGetLastError();
+}
+template <typename Core, bool A_KM, bool B_KN>
+cudaError_t launch_gemm(b200bo_ctx* h, const GemmArgs& g, int M, int N, int batch) {
+  return launch_gemm_on<Core, A_KM, B_KN>(h, h->stream, g, M, N, batch);
+}
+
+template <class F>
+static int run_graphed(b200bo_ctx* h, GraphSlot& slot, const void* const (&key)[8], int& launches, F&& body) {
+  cudaStream_t st = h->stream;
+  // Measured (scripts/fit_time.py): replay wins where the chain is launch-latency bound (N = 1024: Cholesky 0.68 ->
+  // 0.61 ms) and loses slightly at N >= 4096, where the captured nodes no longer carry the helper stream's low priority
+  // and the big trailing GEMMs get in the way of the panel chain (3.06 -> 3.23 ms): eager above ld = 2048.
+  if (h->ld > 2048) {
+    int l = 0;
+    int rc = body(l);
+    launches += l;
+    return rc;
+  }
+  bool same = true;
+  for (int i = 0; i < 8; ++i) same = same && slot.key[i] == key[i];
+  if (!h->use_graphs || !same) {
+    slot.drop();
+    for (int i = 0; i < 8; ++i) slot.key[i] = key[i];
+  }
+  if (h->use_graphs && slot.exec) {
+    CU_TRY(cudaGraphLaunch(slot.exec, st));
+    launches += slot.launches;
+    return 0;
+  }
+  if (!h->use_graphs || slot.seen++ == 0) {  // first sighting: eager (also warms every function attribute)
+    int l = 0;
+    int rc = body(l);
+    launches += l;
+    return rc;
+  }
+  int l = 0;
+  CU_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+  int rc = body(l);
+  cudaGraph_t g = nullptr;
+  cudaError_t e = cudaStreamEndCapture(st, &g);
+  if (rc || e != cudaSuccess || !g) {
+    if (g) cudaGraphDestroy(g);
+    cudaGetLastError();
+    if (rc) return rc;
+    h->use_graphs = 0;  // capture is not available here: stay eager
+    l = 0;
+    rc = body(l);
+    launches += l;
+    return rc;
+  }
+  e = cudaGraphInstantiate(&slot.exec, g, 0);
+  cudaGraphDestroy(g);
+  if (e != cudaSuccess) {
+    slot.exec = nullptr;
+    cudaGetLastError();
+    h->use_graphs = 0;
+    l = 0;
+    rc = body(l);
+    launches += l;
+    return rc;
+  }
+  slot.launches = l;
+  CU_TRY(cudaGraphLaunch(slot.exec, st));
+  launches += l;
+  return 0;
 }
 
 struct PhaseTimer {
@@ -248,6 +334,8 @@ int b200bo_create(int device, b200bo_handle* out) {
   // developer knobs (A/B runs): first-pass products and the mbarrier suspend hint of the fused kernels
   if (const char* e = getenv("B200BO_FAST_PRODUCTS")) h->fast_products = atoi(e) == 3 ? 3 : 1;
   if (const char* e = getenv("B200BO_FAST_KERNEL")) h->fast_kernel_pref = std::max(1, std::min(5, atoi(e)));
+  if (const char* e = getenv("B200BO_CHOL_LOOKAHEAD")) h->lookahead = atoi(e) != 0;
+  if (const char* e = getenv("B200BO_GRAPHS")) h->use_graphs = atoi(e) != 0;
   if (const char* e = getenv("B200BO_REPLAY_MB")) h->replay_mb = std::max(0, std::min(4096, atoi(e)));
   if (const char* e = getenv("B200BO_WAIT_HINT_NS")) {
     unsigned v = (unsigned)atoi(e);
@@ -279,6 +367,11 @@ int b200bo_destroy(b200bo_handle h) {
     if (h->ev_used[i]) cudaEventDestroy(h->ev_used[i]);
   }
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  h->g_chol.drop();
+  h->g_trtri.drop();
+  if (h->la_stream) cudaStreamDestroy(h->la_stream);
+  if (h->inv_stream) cudaStreamDestroy(h->inv_stream);
+  for (cudaEvent_t e : h->la_ev) cudaEventDestroy(e);
   h->evs.destroy();
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -438,32 +531,101 @@ static int factor_impl(b200bo_handle h, int corr, const double* theta, int n_the
   // ---- 2. blocked right-looking Cholesky (lower), fp64 DMMA trailing updates -------------------------
   pt.begin(1);
   CU_TRY(cudaFuncSetAttribute(chol_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHOL_DIAG_SMEM));
+  // Look-ahead of depth one: the trailing update of panel j is split into (a) the next block column -- all the next
+  // diagonal block and panel need -- on the main stream and (b) the rest on a low-priority helper stream, so that
+  // chol_diag(j+1) (one CTA, latency bound) and panel(j+1) run underneath (b) of panel j.  (a) of panel j+1 touches the
+  // block column (b) of panel j also updates: it waits for it.
+  const bool la = h->lookahead && nb > 2;
+  if (la) {
+    if (!h->la_stream) {
+      int lo = 0, hi = 0;
+      CU_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      CU_TRY(cudaStreamCreateWithPriority(&h->la_stream, cudaStreamNonBlocking, lo));
+      CU_TRY(cudaStreamCreateWithPriority(&h->inv_stream, cudaStreamNonBlocking, lo));
+      CU_TRY(cudaFuncSetAttribute(chol_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHOL_FACTOR_SMEM));
+      CU_TRY(cudaFuncSetAttribute(chol_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHOL_DIAG_SMEM));
+      CU_TRY(cudaFuncSetAttribute(panel_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_TRSM_SMEM));
+    }
+    while ((int)h->la_ev.size() < 3 * nb + 1) {
+      cudaEvent_t e;
+      CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      h->la_ev.push_back(e);
+    }
+  }
+  const void* const gkey[8] = {h->A.p, h->W.p, h->S.p, h->Dinv.p, h->status.p, (const void*)(intptr_t)ld,
+                               (const void*)(intptr_t)(la ? 1 : 0), (const void*)st};
+  auto chol_body = [&](int& launches) -> int {
+  int last_b = -1;  // index of the last panel whose (b) part went to the helper stream
   for (int jb = 0; jb < nb; ++jb) {
     double* Ajj = h->A.p + (size_t)jb * NB * (ld + 1);
     double* Dj = h->Dinv.p + (size_t)jb * NB * NB;
-    chol_diag_kernel<<<1, 256, CHOL_DIAG_SMEM, st>>>(Ajj, ld, Dj, h->status.p);
-    CU_TRY(cudaGetLastError());
+    if (la) {
+      // factor on the main stream; the block inverse (only the L^-1 stage needs it) on its own stream
+      chol_factor_kernel<<<1, 256, CHOL_FACTOR_SMEM, st>>>(Ajj, ld, h->status.p);
+      CU_TRY(cudaGetLastError());
+      CU_TRY(cudaEventRecord(h->la_ev[2 * nb + jb], st));
+      CU_TRY(cudaStreamWaitEvent(h->inv_stream, h->la_ev[2 * nb + jb], 0));
+      chol_inverse_kernel<<<1, 256, CHOL_DIAG_SMEM, h->inv_stream>>>(Ajj, ld, Dj);
+      CU_TRY(cudaGetLastError());
+      ++launches;
+    } else {
+      chol_diag_kernel<<<1, 256, CHOL_DIAG_SMEM, st>>>(Ajj, ld, Dj, h->status.p);
+      CU_TRY(cudaGetLastError());
+    }
     ++launches;
     int mrem = ld - (jb + 1) * NB;
     if (mrem > 0) {
       double* P = h->A.p + (size_t)(jb + 1) * NB * ld + (size_t)jb * NB;
-      GemmArgs g{};  // panel: P <- P * Ljj^-T   (C(m,n) = sum_k P(m,k) Dinv(n,k))
-      g.A = P; g.B = Dj; g.C = P; g.lda = ld; g.ldb = NB; g.ldc = ld; g.K = NB; g.alpha = 1.0; g.beta = 0.0;
-      CU_TRY((launch_gemm<GemmNT, false, false>(h, g, mrem, NB, 1)));
+      if (la) {  // panel: P <- P * Ljj^-T by row-parallel substitution against the factor itself
+        panel_trsm_kernel<<<mrem / 64, 64, PANEL_TRSM_SMEM, st>>>(P, ld, Ajj);
+        CU_TRY(cudaGetLastError());
+      } else {
+        GemmArgs g{};  // panel: P <- P * Ljj^-T   (C(m,n) = sum_k P(m,k) Dinv(n,k))
+        g.A = P; g.B = Dj; g.C = P; g.lda = ld; g.ldb = NB; g.ldc = ld; g.K = NB; g.alpha = 1.0; g.beta = 0.0;
+        CU_TRY((launch_gemm<GemmNT, false, false>(h, g, mrem, NB, 1)));
+      }
       GemmArgs s{};  // trailing update: A22 <- A22 - P P^T, lower tiles only
       s.A = P; s.B = P; s.C = h->A.p + (size_t)(jb + 1) * NB * (ld + 1);
       s.lda = ld; s.ldb = ld; s.ldc = ld; s.K = NB; s.alpha = -1.0; s.beta = 1.0; s.lower_only = 1;
-      CU_TRY((launch_gemm<GemmNT, false, false>(h, s, mrem, mrem, 1)));
+      if (!la) {
+        CU_TRY((launch_gemm<GemmNT, false, false>(h, s, mrem, mrem, 1)));
+        launches += 2;
+        continue;
+      }
+      if (last_b >= 0) CU_TRY(cudaStreamWaitEvent(st, h->la_ev[2 * last_b + 1], 0));
+      CU_TRY((launch_gemm<GemmNT, false, false>(h, s, mrem, NB, 1)));  // (a): block column jb + 1
       launches += 2;
+      if (mrem > NB) {
+        CU_TRY(cudaEventRecord(h->la_ev[2 * jb], st));
+        CU_TRY(cudaStreamWaitEvent(h->la_stream, h->la_ev[2 * jb], 0));
+        GemmArgs b = s;  // (b): columns jb + 2 .. of the trailing matrix, from the rows of P below the first block
+        b.A = P + (size_t)NB * ld; b.B = b.A; b.C = s.C + (size_t)NB * (ld + 1);
+        CU_TRY((launch_gemm_on<GemmNT, false, false>(h, h->la_stream, b, mrem - NB, mrem - NB, 1)));
+        CU_TRY(cudaEventRecord(h->la_ev[2 * jb + 1], h->la_stream));
+        last_b = jb;
+        ++launches;
+      }
     }
+  }
+  if (la) {
+    if (last_b >= 0) CU_TRY(cudaStreamWaitEvent(st, h->la_ev[2 * last_b + 1], 0));
+    CU_TRY(cudaEventRecord(h->la_ev[3 * nb], h->inv_stream));  // every diagonal inverse is in place
+    CU_TRY(cudaStreamWaitEvent(st, h->la_ev[3 * nb], 0));
   }
   zero_upper_kernel<<<h->num_sms * 4, 256, 0, st>>>(h->A.p, ld);
   CU_TRY(cudaGetLastError());
   ++launches;
+  return 0;
+  };
+  {
+    int rc = run_graphed(h, h->g_chol, gkey, launches, chol_body);
+    if (rc) return rc;
+  }
   pt.end(1);
 
   // ---- 3. L^-1 by recursive doubling: [[A,0],[B,C]]^-1 = [[A^-1,0],[-C^-1 B A^-1, C^-1]] -------------
   pt.begin(2);
+  auto trtri_body = [&](int& launches) -> int {
   CU_TRY(cudaMemsetAsync(h->W.p, 0, nn * 8, st));
   scatter_dinv_kernel<<<nb, 256, 0, st>>>(h->Dinv.p, h->W.p, ld);
   CU_TRY(cudaGetLastError());
@@ -499,6 +661,12 @@ static int factor_impl(b200bo_handle h, int corr, const double* theta, int n_the
       int rc = merge(gf * 2 * s, rem - s, 1);
       if (rc) return rc;
     }
+  }
+  return 0;
+  };
+  {
+    int rc = run_graphed(h, h->g_trtri, gkey, launches, trtri_body);
+    if (rc) return rc;
   }
   pt.end(2);
 

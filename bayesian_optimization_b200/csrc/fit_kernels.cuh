@@ -221,6 +221,150 @@ __global__ void __launch_bounds__(256) chol_diag_kernel(double* __restrict__ A, 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Split form of the diagonal step for the look-ahead Cholesky: only the FACTORISATION of the 64 x 64 block and the
+// panel solve against it sit on the critical path; the block inverse (level 0 of the recursive L^-1) runs on a helper
+// stream whenever the factor is there.
+// ---------------------------------------------------------------------------------------------------
+constexpr size_t CHOL_FACTOR_SMEM = (NB * (NB + 1) + 3 * NB) * sizeof(double);
+
+// factor A[jb,jb] = Ljj Ljj^T, write Ljj back (strict upper triangle zeroed).  Same arithmetic as chol_diag_kernel.
+__global__ void __launch_bounds__(256) chol_factor_kernel(double* __restrict__ A, int ld, int* __restrict__ status) {
+  extern __shared__ __align__(16) double sm_cf[];
+  double(*s)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(sm_cf);
+  double* rs = sm_cf + NB * (NB + 1);
+  double* colbuf = rs + NB;  // [2][NB]
+  const int tid = threadIdx.x;
+  const int tr = tid >> 4, tc = tid & 15;
+  double a[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) a[i][k] = A[(size_t)(tr + 16 * i) * ld + tc + 16 * k];
+#pragma unroll
+  for (int kj = 0; kj < 4; ++kj) {
+#pragma unroll 1
+    for (int jj = 0; jj < 16; ++jj) {
+      const int j = 16 * kj + jj;
+      double* cb = colbuf + (j & 1) * NB;
+      if (tc == jj) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) cb[tr + 16 * i] = a[i][kj];
+      }
+      __syncthreads();
+      const double dinv = __drcp_rn(cb[j]);
+      double li[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) li[i] = cb[tr + 16 * i] * dinv;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (k < kj) continue;
+        const int c = tc + 16 * k;
+        if (c > j) {
+          const double lc = cb[c];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (tr + 16 * i >= c) a[i][k] = fma(-li[i], lc, a[i][k]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s[tr + 16 * i][tc + 16 * k] = a[i][k];
+  __syncthreads();
+  if (tid < NB) {
+    const double d = s[tid][tid];
+    if (!(d > 16.0 * 2.220446049250313e-16)) atomicOr(status, 1);  // see chol_diag_kernel
+    rs[tid] = 1.0 / sqrt(d);
+  }
+  __syncthreads();
+  for (int e = tid; e < NB * NB; e += 256) {
+    const int r = e / NB, c = e % NB;
+    A[(size_t)r * ld + c] = r >= c ? s[r][c] * rs[c] : 0.0;
+  }
+}
+
+// inverse of the factored diagonal block (16 -> 32 -> 64 block recursion, as in chol_diag_kernel) -> Dinv
+__global__ void __launch_bounds__(256) chol_inverse_kernel(const double* __restrict__ A, int ld, double* __restrict__ Dinv) {
+  extern __shared__ __align__(16) double sm_ci[];
+  double(*s)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(sm_ci);
+  double(*x)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(sm_ci + NB * (NB + 1));
+  double(*t)[33] = reinterpret_cast<double(*)[33]>(sm_ci + 2 * NB * (NB + 1));
+  double* rs = sm_ci + 2 * NB * (NB + 1) + 32 * 33;
+  const int tid = threadIdx.x;
+  for (int e = tid; e < NB * NB; e += 256) {
+    const int r = e / NB, c = e % NB;
+    s[r][c] = A[(size_t)r * ld + c];
+    x[r][c] = 0.0;
+  }
+  __syncthreads();
+  if (tid < NB) rs[tid] = 1.0 / s[tid][tid];
+  __syncthreads();
+  if (tid < NB) {
+    const int c = tid, b0 = c & ~15;
+    x[c][c] = rs[c];
+    for (int r = c + 1; r < b0 + 16; ++r) {
+      double acc = 0.0;
+      for (int k = c; k < r; ++k) acc += s[r][k] * x[k][c];
+      x[r][c] = -acc * rs[r];
+    }
+  }
+  __syncthreads();
+  for (int half = 16; half < NB; half *= 2) {
+    const int nblk = NB / (2 * half);
+    const int per = half * half;
+    for (int e = tid; e < nblk * per; e += 256) {
+      const int q = e / per, i = (e % per) / half, jj = e % half;
+      const int o = q * 2 * half;
+      double acc = 0.0;
+      for (int k = jj; k < half; ++k) acc += s[o + half + i][o + k] * x[o + k][o + jj];
+      t[q * half + i][jj] = acc;
+    }
+    __syncthreads();
+    for (int e = tid; e < nblk * per; e += 256) {
+      const int q = e / per, i = (e % per) / half, jj = e % half;
+      const int o = q * 2 * half;
+      double acc = 0.0;
+      for (int k = 0; k <= i; ++k) acc += x[o + half + i][o + half + k] * t[q * half + k][jj];
+      x[o + half + i][o + jj] = -acc;
+    }
+    __syncthreads();
+  }
+  for (int e = tid; e < NB * NB; e += 256) Dinv[e] = x[e / NB][e % NB];
+}
+
+// panel solve P <- P Ljj^-T by substitution, one thread per row of P (rows are independent; right-looking form so the
+// 63 - c updates after each pivot are independent FMAs).  grid = rows / 64.
+constexpr size_t PANEL_TRSM_SMEM = (NB * (NB + 1) + NB) * sizeof(double);
+__global__ void __launch_bounds__(64) panel_trsm_kernel(double* __restrict__ P, int ld, const double* __restrict__ Ljj) {
+  extern __shared__ __align__(16) double sm_pt[];
+  double(*L)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(sm_pt);
+  double* rd = sm_pt + NB * (NB + 1);
+  const int tid = threadIdx.x;
+  for (int e = tid; e < NB * NB; e += 64) L[e % NB][e / NB] = Ljj[(size_t)(e / NB) * ld + e % NB];  // L^T: L[c][j] = Ljj[j][c]
+  __syncthreads();
+  if (tid < NB) rd[tid] = 1.0 / L[tid][tid];
+  __syncthreads();
+  double* row = P + (size_t)(blockIdx.x * 64 + tid) * ld;
+  double x[NB];
+#pragma unroll
+  for (int c = 0; c < NB; c += 2) {
+    const double2 v = *reinterpret_cast<const double2*>(row + c);
+    x[c] = v.x;
+    x[c + 1] = v.y;
+  }
+#pragma unroll
+  for (int c = 0; c < NB; ++c) {
+    x[c] *= rd[c];
+#pragma unroll
+    for (int j = c + 1; j < NB; ++j) x[j] = fma(-x[c], L[c][j], x[j]);  // L[c][j] = Ljj[j][c]: broadcast read
+  }
+#pragma unroll
+  for (int c = 0; c < NB; c += 2) *reinterpret_cast<double2*>(row + c) = make_double2(x[c], x[c + 1]);
+}
+
 // W[jb,jb] = Dinv[jb] for every diagonal block (level 0 of the recursive triangular inverse)
 __global__ void scatter_dinv_kernel(const double* __restrict__ Dinv, double* __restrict__ W, int ld) {
   int jb = blockIdx.x;
