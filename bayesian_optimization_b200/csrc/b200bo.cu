@@ -172,7 +172,10 @@ struct b200bo_ctx {
   cudaStream_t la_stream = nullptr;  // low-priority helper stream of the Cholesky look-ahead
   cudaStream_t inv_stream = nullptr; // diagonal-block inverses, off the critical path
   std::vector<cudaEvent_t> la_ev;    // 3 events per panel (untimed)
-  int lookahead = 1;
+  int lookahead = 2;  // 0: single stream; 1: look-ahead with separate factor / solve / update kernels; 2: one kernel per
+                      // panel step where that measured faster (N <= 2048: 0.53 vs 0.59 ms at N = 1024; at N >= 4096 the
+                      // fused step is 38 us against ~35 us for the three small kernels, 3.2 vs 3.04 ms), else as 1
+  DevBuf<double> Lside, P0side;
   int use_graphs = 1;
   GraphSlot g_chol, g_trtri;
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_used[2] = {nullptr, nullptr};
@@ -334,7 +337,7 @@ int b200bo_create(int device, b200bo_handle* out) {
   // developer knobs (A/B runs): first-pass products and the mbarrier suspend hint of the fused kernels
   if (const char* e = getenv("B200BO_FAST_PRODUCTS")) h->fast_products = atoi(e) == 3 ? 3 : 1;
   if (const char* e = getenv("B200BO_FAST_KERNEL")) h->fast_kernel_pref = std::max(1, std::min(5, atoi(e)));
-  if (const char* e = getenv("B200BO_CHOL_LOOKAHEAD")) h->lookahead = atoi(e) != 0;
+  if (const char* e = getenv("B200BO_CHOL_LOOKAHEAD")) h->lookahead = std::max(0, std::min(2, atoi(e)));
   if (const char* e = getenv("B200BO_GRAPHS")) h->use_graphs = atoi(e) != 0;
   if (const char* e = getenv("B200BO_REPLAY_MB")) h->replay_mb = std::max(0, std::min(4096, atoi(e)));
   if (const char* e = getenv("B200BO_WAIT_HINT_NS")) {
@@ -545,7 +548,11 @@ static int factor_impl(b200bo_handle h, int corr, const double* theta, int n_the
       CU_TRY(cudaFuncSetAttribute(chol_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHOL_FACTOR_SMEM));
       CU_TRY(cudaFuncSetAttribute(chol_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHOL_DIAG_SMEM));
       CU_TRY(cudaFuncSetAttribute(panel_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_TRSM_SMEM));
+      CU_TRY(cudaFuncSetAttribute(panel_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_CHAIN_SMEM));
+      CU_TRY(cudaFuncSetAttribute(chol_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHOL_DIAG_SMEM));
     }
+    CU_TRY(h->Lside.reserve((size_t)nb * NB * NB));
+    CU_TRY(h->P0side.reserve((size_t)nb * NB * NB));
     while ((int)h->la_ev.size() < 3 * nb + 1) {
       cudaEvent_t e;
       CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -553,9 +560,36 @@ static int factor_impl(b200bo_handle h, int corr, const double* theta, int n_the
     }
   }
   const void* const gkey[8] = {h->A.p, h->W.p, h->S.p, h->Dinv.p, h->status.p, (const void*)(intptr_t)ld,
-                               (const void*)(intptr_t)(la ? 1 : 0), (const void*)st};
+                               (const void*)(intptr_t)(la ? (h->lookahead >= 2 && ld <= 2048 ? 2 : 1) : 0), (const void*)st};
   auto chol_body = [&](int& launches) -> int {
   int last_b = -1;  // index of the last panel whose (b) part went to the helper stream
+  if (la && h->lookahead >= 2 && ld <= 2048) {
+    // one kernel per panel step on the main stream (update of block column jb by panel jb - 1, factor, solve); the
+    // rest of panel jb's trailing update (b) and the block inverse / write-backs on the helper streams.  Step jb reads
+    // block column jb, which (b) of every panel <= jb - 2 has updated: it waits for the last of them.
+    for (int jb = 0; jb < nb; ++jb) {
+      const int nrows = nb - 1 - jb;
+      if (jb >= 2 && last_b >= 0) CU_TRY(cudaStreamWaitEvent(st, h->la_ev[2 * std::min(last_b, jb - 2) + 1], 0));
+      panel_chain_kernel<<<std::max(nrows, 1), 256, PANEL_CHAIN_SMEM, st>>>(h->A.p, ld, jb, nrows, h->Lside.p, h->P0side.p, h->status.p);
+      CU_TRY(cudaGetLastError());
+      CU_TRY(cudaEventRecord(h->la_ev[2 * jb], st));
+      CU_TRY(cudaStreamWaitEvent(h->inv_stream, h->la_ev[2 * jb], 0));
+      chol_finish_kernel<<<1, 256, CHOL_DIAG_SMEM, h->inv_stream>>>(h->A.p, ld, jb, nrows, h->Lside.p, h->P0side.p, h->Dinv.p);
+      CU_TRY(cudaGetLastError());
+      launches += 2;
+      if (nrows >= 2) {
+        CU_TRY(cudaStreamWaitEvent(h->la_stream, h->la_ev[2 * jb], 0));
+        double* P1 = h->A.p + (size_t)(jb + 2) * NB * ld + (size_t)jb * NB;  // rows of panel jb below its first block
+        GemmArgs bq{};
+        bq.A = P1; bq.B = P1; bq.C = h->A.p + (size_t)(jb + 2) * NB * (ld + 1);
+        bq.lda = ld; bq.ldb = ld; bq.ldc = ld; bq.K = NB; bq.alpha = -1.0; bq.beta = 1.0; bq.lower_only = 1;
+        CU_TRY((launch_gemm_on<GemmNT, false, false>(h, h->la_stream, bq, (nrows - 1) * NB, (nrows - 1) * NB, 1)));
+        CU_TRY(cudaEventRecord(h->la_ev[2 * jb + 1], h->la_stream));
+        last_b = jb;
+        ++launches;
+      }
+    }
+  } else
   for (int jb = 0; jb < nb; ++jb) {
     double* Ajj = h->A.p + (size_t)jb * NB * (ld + 1);
     double* Dj = h->Dinv.p + (size_t)jb * NB * NB;

@@ -365,6 +365,215 @@ __global__ void __launch_bounds__(64) panel_trsm_kernel(double* __restrict__ P, 
   for (int c = 0; c < NB; c += 2) *reinterpret_cast<double2*>(row + c) = make_double2(x[c], x[c + 1]);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// One panel step of the look-ahead Cholesky as ONE kernel: the latency chain "update the next block column ->
+// factor its diagonal block -> solve the panel against it" used to be three dependent launches per panel.
+// CTA b of step j owns row block b of panel j (global row block j + 1 + b) and does, entirely on chip:
+//   (a) the step-(j-1) update of what it needs of block column j:   Dg -= Q0 Q0^T,  Xb -= Qb Q0^T
+//       (Q* = rows of the previous solved panel; the diagonal block Dg is updated redundantly by every CTA),
+//   (f) the factorisation Dg = L L^T (redundantly: 64 sequential columns either way),
+//   (s) its own rows  Pb = Xb L^-T  by substitution (one thread per row).
+// Nothing a neighbour still has to read is overwritten: the factor goes to Lside[j] and the first solved row block to
+// P0side[j] (chol_finish_kernel moves both into A once the step is over); row blocks b >= 1 go straight into A.
+// ---------------------------------------------------------------------------------------------------
+constexpr int PC_TS = NB * (NB + 1);  // one padded 64 x 64 tile
+constexpr size_t PANEL_CHAIN_SMEM = (4 * PC_TS + 3 * NB) * sizeof(double);
+
+__global__ void __launch_bounds__(256, 1)
+panel_chain_kernel(double* __restrict__ A, int ld, int jb, int nrows, double* __restrict__ Lside,
+                   double* __restrict__ P0side, int* __restrict__ status) {
+  extern __shared__ __align__(16) double sm_pc[];
+  double(*sD)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(sm_pc);               // Dg -> L
+  double(*sQ0)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(sm_pc + PC_TS);      // previous panel, rows of block j
+  double(*sX)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(sm_pc + 2 * PC_TS);   // own rows of panel j
+  double(*sQ)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(sm_pc + 3 * PC_TS);   // previous panel, own rows
+  double* rs = sm_pc + 4 * PC_TS;
+  double* colbuf = rs + NB;  // [2][NB]
+  const int tid = threadIdx.x, b = blockIdx.x;
+  const bool has_rows = b < nrows;   // the last step has no panel: one CTA factors the last diagonal block
+  const bool has_prev = jb > 0;
+  const double* Dg = A + (size_t)jb * NB * (ld + 1);
+  double* Xb = A + (size_t)(jb + 1 + b) * NB * ld + (size_t)jb * NB;
+  const double* Q0 = P0side + (size_t)(jb - 1) * NB * NB;                                   // (64, 64) row-major
+  const double* Qb = A + (size_t)(jb + 1 + b) * NB * ld + (size_t)(jb - 1) * NB;
+  for (int e = tid; e < NB * NB; e += 256) {
+    const int r = e / NB, c = e % NB;
+    sD[r][c] = Dg[(size_t)r * ld + c];
+    if (has_prev) sQ0[r][c] = Q0[e];
+    if (has_rows) {
+      sX[r][c] = Xb[(size_t)r * ld + c];
+      if (has_prev) sQ[r][c] = Qb[(size_t)r * ld + c];
+    }
+  }
+  __syncthreads();
+  const int tr = tid >> 4, tc = tid & 15;
+  // ---- (a) + register tile of the diagonal block: thread (tr, tc) holds (tr + 16 i, tc + 16 k)
+  double a[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) a[i][k] = sD[tr + 16 * i][tc + 16 * k];
+  if (has_prev) {
+    double x[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) x[i][k] = has_rows ? sX[tr + 16 * i][tc + 16 * k] : 0.0;
+#pragma unroll 4
+    for (int kk = 0; kk < NB; ++kk) {
+      double qr[4], qc[4], qx[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        qr[i] = sQ0[tr + 16 * i][kk];
+        qc[i] = sQ0[tc + 16 * i][kk];
+        qx[i] = has_rows ? sQ[tr + 16 * i][kk] : 0.0;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          a[i][k] = fma(-qr[i], qc[k], a[i][k]);
+          x[i][k] = fma(-qx[i], qc[k], x[i][k]);
+        }
+    }
+    __syncthreads();
+    if (has_rows) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) sX[tr + 16 * i][tc + 16 * k] = x[i][k];
+    }
+  }
+  // ---- (f) right-looking factorisation on unscaled columns (chol_factor_kernel's arithmetic)
+#pragma unroll
+  for (int kj = 0; kj < 4; ++kj) {
+#pragma unroll 1
+    for (int jj = 0; jj < 16; ++jj) {
+      const int j = 16 * kj + jj;
+      double* cb = colbuf + (j & 1) * NB;
+      if (tc == jj) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) cb[tr + 16 * i] = a[i][kj];
+      }
+      __syncthreads();
+      const double dinv = __drcp_rn(cb[j]);
+      double li[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) li[i] = cb[tr + 16 * i] * dinv;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (k < kj) continue;
+        const int c = tc + 16 * k;
+        if (c > j) {
+          const double lc = cb[c];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (tr + 16 * i >= c) a[i][k] = fma(-li[i], lc, a[i][k]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) sD[tr + 16 * i][tc + 16 * k] = a[i][k];
+  __syncthreads();
+  if (tid < NB) {
+    const double d = sD[tid][tid];
+    if (b == 0 && !(d > 16.0 * 2.220446049250313e-16)) atomicOr(status, 1);  // see chol_diag_kernel
+    rs[tid] = 1.0 / sqrt(d);
+  }
+  __syncthreads();
+  for (int e = tid; e < NB * NB; e += 256) {
+    const int r = e / NB, c = e % NB;
+    const double v = r >= c ? sD[r][c] * rs[c] : 0.0;
+    sD[r][c] = v;
+    if (b == 0) Lside[(size_t)jb * NB * NB + e] = v;
+  }
+  __syncthreads();
+  if (!has_rows) return;
+  // ---- (s) own rows: x L^T = p, right-looking.  Four threads per row (columns 4 m + q, interleaved so the work stays
+  // balanced as the pivot advances); the pivot value travels by shuffle.  One thread per row would be 2016 straight-line
+  // FMAs executed once -- instruction-fetch bound (measured 18 us for the 64 x 64 block).
+  {
+    const int r = tid >> 2, q = tid & 3, lane = tid & 31;
+    double x[16];
+#pragma unroll
+    for (int m = 0; m < 16; ++m) x[m] = sX[r][4 * m + q];
+#pragma unroll
+    for (int c = 0; c < NB; ++c) {
+      const int mc = c >> 2, qc = c & 3;
+      const double xc = __shfl_sync(0xffffffffu, x[mc] * rs[c], (lane & ~3) | qc);   // 1 / L_cc = rs[c]
+      if (q == qc) x[mc] = xc;
+      if (q > qc) x[mc] = fma(-xc, sD[4 * mc + q][c], x[mc]);
+#pragma unroll
+      for (int m = mc + 1; m < 16; ++m) x[m] = fma(-xc, sD[4 * m + q][c], x[m]);
+    }
+#pragma unroll
+    for (int m = 0; m < 16; ++m) sX[r][4 * m + q] = x[m];
+  }
+  __syncthreads();
+  double* out = b == 0 ? P0side + (size_t)jb * NB * NB : Xb;
+  const int old = b == 0 ? NB : ld;
+  for (int e = tid; e < NB * NB; e += 256) out[(size_t)(e / NB) * old + e % NB] = sX[e / NB][e % NB];
+}
+
+// after a panel step: the factor and the first solved row block move into A, and the block inverse (level 0 of the
+// recursive L^-1) is formed -- all off the critical path
+__global__ void __launch_bounds__(256) chol_finish_kernel(double* __restrict__ A, int ld, int jb, int nrows,
+                                                          const double* __restrict__ Lside, const double* __restrict__ P0side,
+                                                          double* __restrict__ Dinv) {
+  extern __shared__ __align__(16) double sm_cf2[];
+  double(*s)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(sm_cf2);
+  double(*x)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(sm_cf2 + NB * (NB + 1));
+  double(*t)[33] = reinterpret_cast<double(*)[33]>(sm_cf2 + 2 * NB * (NB + 1));
+  double* rs = sm_cf2 + 2 * NB * (NB + 1) + 32 * 33;
+  const int tid = threadIdx.x;
+  double* Ajj = A + (size_t)jb * NB * (ld + 1);
+  for (int e = tid; e < NB * NB; e += 256) {
+    const int r = e / NB, c = e % NB;
+    const double v = Lside[(size_t)jb * NB * NB + e];
+    s[r][c] = v;
+    x[r][c] = 0.0;
+    Ajj[(size_t)r * ld + c] = v;
+    if (nrows > 0) A[(size_t)((jb + 1) * NB + r) * ld + (size_t)jb * NB + c] = P0side[(size_t)jb * NB * NB + e];
+  }
+  __syncthreads();
+  if (tid < NB) rs[tid] = 1.0 / s[tid][tid];
+  __syncthreads();
+  if (tid < NB) {
+    const int c = tid, b0 = c & ~15;
+    x[c][c] = rs[c];
+    for (int r = c + 1; r < b0 + 16; ++r) {
+      double acc = 0.0;
+      for (int k = c; k < r; ++k) acc += s[r][k] * x[k][c];
+      x[r][c] = -acc * rs[r];
+    }
+  }
+  __syncthreads();
+  for (int half = 16; half < NB; half *= 2) {
+    const int nblk = NB / (2 * half);
+    const int per = half * half;
+    for (int e = tid; e < nblk * per; e += 256) {
+      const int q = e / per, i = (e % per) / half, jj = e % half;
+      const int o = q * 2 * half;
+      double acc = 0.0;
+      for (int k = jj; k < half; ++k) acc += s[o + half + i][o + k] * x[o + k][o + jj];
+      t[q * half + i][jj] = acc;
+    }
+    __syncthreads();
+    for (int e = tid; e < nblk * per; e += 256) {
+      const int q = e / per, i = (e % per) / half, jj = e % half;
+      const int o = q * 2 * half;
+      double acc = 0.0;
+      for (int k = 0; k <= i; ++k) acc += x[o + half + i][o + half + k] * t[q * half + k][jj];
+      x[o + half + i][o + jj] = -acc;
+    }
+    __syncthreads();
+  }
+  for (int e = tid; e < NB * NB; e += 256) Dinv[(size_t)jb * NB * NB + e] = x[e / NB][e % NB];
+}
+
 // W[jb,jb] = Dinv[jb] for every diagonal block (level 0 of the recursive triangular inverse)
 __global__ void scatter_dinv_kernel(const double* __restrict__ Dinv, double* __restrict__ W, int ld) {
   int jb = blockIdx.x;
