@@ -202,8 +202,11 @@ predict_fused_decoupled_kernel(const __grid_constant__ fk4::ReplayMaps rmaps, co
           const int kext = min(ld, WC * (s + 1));
           const int n0 = WC * s;
           const bool act_2 = n0 + NBA < ld;
-          for (int k0 = 0; k0 < kext; k0 += KC, ++it) {
-            const int kc = k0 / KC;
+          const int n_bulk = n0 / KC;                               // replayed chunks under full blocks
+          const bool desc = ((n_super - 1 - s) & 1) != 0;           // sawtooth: see the main-MMA warp
+          for (int ci = 0; ci < kext / KC; ++ci, ++it) {
+            const int kc = ci < n_bulk ? (desc ? n_bulk - 1 - ci : ci) : ci;
+            const int k0 = kc * KC;
             mbar_wait_fast(BAR(BAR_EMPTY_ST + st), ph ^ 1, p.err, 1);
             // the MMAs of use it - ST have retired: tell the producers (they reuse scratch slots of the previous tile)
             if (el && it >= (uint32_t)ST) st_release_cta(cons_cnt, it - ST + 1);
@@ -338,7 +341,16 @@ predict_fused_decoupled_kernel(const __grid_constant__ fk4::ReplayMaps rmaps, co
           const int n0 = WC * s;
           const bool has2 = n0 + NBA < ld;
           const uint32_t pe = (ist & 1) ^ 1;
-          for (int k0 = 0; k0 < kext; k0 += KC, ++ic) {
+          // Sawtooth over the replayed chunks: every other super-tile walks them downwards, so that a super-tile starts
+          // with the chunks the previous one touched last and the scratch (148 MB at N = 4096, cyclic reads thrash an
+          // LRU-like 126 MB L2) is re-read in most-recently-used order.  The diagonal chunks stay last and ascending (the
+          // block-final commits depend on it) and the LAST super-tile ascends, so that the slots of the low chunks are
+          // released first and the producers keep their head start on the next tile.
+          const int n_bulk = n0 / KC;
+          const bool desc = ((n_super - 1 - s) & 1) != 0;
+          for (int ci = 0; ci < kext / KC; ++ci, ++ic) {
+            const int k0 = (ci < n_bulk ? (desc ? n_bulk - 1 - ci : ci) : ci) * KC;
+            const bool first = ci == 0;   // first chunk of the super-tile: overwrite the accumulators
             const uint32_t nst = (st + 1) & (ST - 1), nph = ph ^ (nst == 0 ? 1u : 0u);
             const bool tr = TRACE && p.trace && blockIdx.x == 0 && ic < (uint32_t)TRACE5_CHUNKS && lane == 0;
             if (tr) p.trace[ic * 8 + 0] = clock64();
@@ -346,7 +358,7 @@ predict_fused_decoupled_kernel(const __grid_constant__ fk4::ReplayMaps rmaps, co
             const uint64_t db_hi = db0 + B_STEP * st, db_lo = db_hi + (BOFF_A_LO >> 4);
             const uint64_t db2_hi = db_hi + (BOFF_B_HI >> 4), db2_lo = db_hi + (BOFF_B_LO >> 4);
             --left;
-            if (k0 != 0 && k0 < n0 && has2) {
+            if (!first && k0 < n0 && has2) {
               // ---- bulk: a replayed chunk under three full blocks
               tc_fence_after();
               if (el) {
@@ -375,7 +387,7 @@ predict_fused_decoupled_kernel(const __grid_constant__ fk4::ReplayMaps rmaps, co
               }
             } else {
               // ---- first chunk of a super-tile, diagonal chunks, partial last super-tile
-              if (k0 == 0) {  // blocks 0 and 1 of the previous super-tile have been drained (long ago, normally)
+              if (first) {  // blocks 0 and 1 of the previous super-tile have been drained (long ago, normally)
                 mbar_wait(BAR(BAR_ACC_EMPTY + 0), pe, p.err, 2);
                 mbar_wait(BAR(BAR_ACC_EMPTY + 1), pe, p.err, 2);
               }
@@ -389,7 +401,7 @@ predict_fused_decoupled_kernel(const __grid_constant__ fk4::ReplayMaps rmaps, co
 #pragma unroll
                 for (int ks = 0; ks < KC / 16; ++ks) {
                   const uint64_t o = (uint64_t)(ks * 2);
-                  umma_f16_pair_p(td, da_hi + o, db_hi + o, idesc, (k0 | ks) != 0, el);
+                  umma_f16_pair_p(td, da_hi + o, db_hi + o, idesc, !first || ks != 0, el);
                   if (NPROD == 3) {
                     umma_f16_pair_p(td, da_hi + o, db_lo + o, idesc, 1, el);
                     umma_f16_pair_p(td, da_lo + o, db_hi + o, idesc, 1, el);
@@ -401,12 +413,12 @@ predict_fused_decoupled_kernel(const __grid_constant__ fk4::ReplayMaps rmaps, co
               // the next chunk's operands: wait for them now, underneath the MMAs just queued
               if (left) mbar_wait_fast(BAR(BAR_FULL + nst), nph, p.err, 3);
               if (has2) {
-                if (k0 == 0) mbar_wait(BAR(BAR_ACC_EMPTY + 2), pe, p.err, 2);
+                if (first) mbar_wait(BAR(BAR_ACC_EMPTY + 2), pe, p.err, 2);
                 tc_fence_after();
 #pragma unroll
                 for (int ks = 0; ks < KC / 16; ++ks) {
                   const uint64_t o = (uint64_t)(ks * 2);
-                  umma_f16_pair_p(tmem_base + (uint32_t)NBA, da_hi + o, db2_hi + o, idesc_128, (k0 | ks) != 0, el);
+                  umma_f16_pair_p(tmem_base + (uint32_t)NBA, da_hi + o, db2_hi + o, idesc_128, !first || ks != 0, el);
                   if (NPROD == 3) {
                     umma_f16_pair_p(tmem_base + (uint32_t)NBA, da_hi + o, db2_lo + o, idesc_128, 1, el);
                     umma_f16_pair_p(tmem_base + (uint32_t)NBA, da_lo + o, db2_hi + o, idesc_128, 1, el);
