@@ -100,6 +100,32 @@ __device__ __forceinline__ void umma_commit_pair_p(uint32_t bar, uint32_t pred) 
 __device__ __forceinline__ void tma_load_2d_pair_p(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar_cluster, uint32_t pred) {
   if (pred) tma_load_2d_pair(dst, map, c0, c1, bar_cluster);
 }
+// TMA load with an L2 eviction-priority hint (createpolicy): the fp16 L^-1 is shared by every SM and re-read 66 times per
+// tile -> evict_last; a scratch chunk is dead after its replay in the last super-tile of the tile -> evict_first there.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_normal() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void tma_load_2d_pair_hint(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar_cluster,
+                                                      uint64_t pol, uint32_t pred) {
+  if (pred)
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%2, %3}], [%4], %5;"
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar_cluster), "l"(pol)
+        : "memory");
+}
 // arrive.expect_tx on the leader's copy of a barrier (address already mapped into the leader's window for the peer)
 __device__ __forceinline__ void mbar_expect_tx_cluster_p(uint32_t bar_cluster, uint32_t bytes, uint32_t pred) {
   if (pred) asm volatile("mbarrier.arrive.expect_tx.relaxed.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(bar_cluster), "r"(bytes) : "memory");
@@ -196,6 +222,7 @@ predict_fused_decoupled_kernel(const __grid_constant__ fk4::ReplayMaps rmaps, co
       const uint32_t el = elect_one_sync() ? 1u : 0u;
       const uint32_t a_bytes = (uint32_t)(PLANES * A_HALF_BYTES);
       const uint32_t full0 = LBAR(BAR_FULL);
+      const uint64_t pol_keep = l2_policy_evict_last(), pol_norm = l2_policy_evict_normal(), pol_dead = l2_policy_evict_first();
       uint32_t it = 0, tl = 0, st = 0, ph = 0;
       for (long long pt = pair; pt < n_ptiles; pt += n_pairs, ++tl)
         for (int s = 0; s < n_super; ++s) {
@@ -215,13 +242,14 @@ predict_fused_decoupled_kernel(const __grid_constant__ fk4::ReplayMaps rmaps, co
             const uint32_t dst = sbase + OFF_B + st * B_STRIDE;
             if (k0 < n0 && act_2) {
               // replay under full blocks: A + 128 rows of blocks 0+1 + 64 rows of block 2
+              const uint64_t pol_a = s == n_super - 1 ? pol_dead : pol_norm;   // last replay of this chunk in this tile
               mbar_expect_tx_cluster_p(fb, a_bytes + (uint32_t)((BA_PLANE + BB_PLANE) * PLANES), el);
-              tma_load_2d_pair_p(da, &rmaps.scr, 0, scr_row(kc, 0), fb, el);
-              if (NPROD == 3) tma_load_2d_pair_p(da + A_HALF_BYTES, &rmaps.scr, 0, scr_row(kc, 1), fb, el);
-              tma_load_2d_pair_p(dst, &maps.hi128, k0, n0 + (int)rank * (NBA / 2), fb, el);
-              if (NPROD == 3) tma_load_2d_pair_p(dst + BOFF_A_LO, &maps.lo128, k0, n0 + (int)rank * (NBA / 2), fb, el);
-              tma_load_2d_pair_p(dst + BOFF_B_HI, &maps.hi64, k0, n0 + NBA + (int)rank * (NBB / 2), fb, el);
-              if (NPROD == 3) tma_load_2d_pair_p(dst + BOFF_B_LO, &maps.lo64, k0, n0 + NBA + (int)rank * (NBB / 2), fb, el);
+              tma_load_2d_pair_hint(da, &rmaps.scr, 0, scr_row(kc, 0), fb, pol_a, el);
+              if (NPROD == 3) tma_load_2d_pair_hint(da + A_HALF_BYTES, &rmaps.scr, 0, scr_row(kc, 1), fb, pol_a, el);
+              tma_load_2d_pair_hint(dst, &maps.hi128, k0, n0 + (int)rank * (NBA / 2), fb, pol_keep, el);
+              if (NPROD == 3) tma_load_2d_pair_hint(dst + BOFF_A_LO, &maps.lo128, k0, n0 + (int)rank * (NBA / 2), fb, pol_keep, el);
+              tma_load_2d_pair_hint(dst + BOFF_B_HI, &maps.hi64, k0, n0 + NBA + (int)rank * (NBB / 2), fb, pol_keep, el);
+              if (NPROD == 3) tma_load_2d_pair_hint(dst + BOFF_B_LO, &maps.lo64, k0, n0 + NBA + (int)rank * (NBB / 2), fb, pol_keep, el);
             } else {
               if (k0 >= n0) {  // first use of this chunk in this tile: the producers must have stored it
                 spin_until_ge(prod_cnt + 4u * (uint32_t)(kc & 1), tl * (uint32_t)(nch / 2) + (uint32_t)(kc / 2) + 1u, p.err, 14);
