@@ -27,8 +27,8 @@ sys.path.insert(0, ROOT)
 
 METRIC = "gp_predict_acq_candidates_per_sec"
 # dram__bytes_read.sum + dram__bytes_write.sum PER CANDIDATE of the fused kernel (generation 5) from the ncu --set full
-# capture of a 75776-candidate launch (profiles/r01/gen5_ncu_summary.txt): the r scratch (148 MB at C3) does not fit L2
-NCU_TRAFFIC_PER_CAND = {("C3", 1): (2.580312e9 + 643.5e6) / 75776}
+# capture of a 75776-candidate launch (profiles/r01/gen5_final_ncu_summary.txt): the r scratch (148 MB at C3) does not fit L2
+NCU_TRAFFIC_PER_CAND = {("C3", 1): (2.047070e9 + 649.5e6) / 75776}
 UNIT = "candidates/s"
 
 
