@@ -114,3 +114,36 @@ def test_pickle_drops_device_handle():
     g2 = pickle.loads(pickle.dumps(gp))
     assert g2._engine is None and g2._cache == {}
     assert g2.estimation_mode == gp.estimation_mode and g2.mean.beta is None
+
+
+def test_trend_classes_match_oracle_basis():
+    """linear / quadratic bases (trend.py:94-142) against the oracle's restatement; (p, k) beta for multi-target fits"""
+    from oracle import gp_oracle as go
+
+    rng = np.random.default_rng(0)
+    X = rng.uniform(-1, 1, (7, 3))
+    np.testing.assert_array_equal(b2.linear_trend(3).F(X), go.trend_basis(go.TREND_LINEAR, X))
+    np.testing.assert_array_equal(b2.quadratic_trend(3).F(X), go.trend_basis(go.TREND_QUADRATIC, X))
+    assert b2.quadratic_trend(3).n_dim == 10 and b2.linear_trend(3).n_dim == 4
+    assert b2.linear_trend(3).Jacobian(X[:1]).shape == (4, 3)
+    with pytest.raises(NotImplementedError):
+        b2.quadratic_trend(3).Jacobian(X[:1])
+    t = b2.linear_trend(3, beta=0.5)
+    assert t.beta.shape == (4, 1) and t(X).shape == (7, 1)
+    with pytest.raises(Exception, match="Shapes"):
+        b2.linear_trend(3, beta=[1.0, 2.0])
+    c = b2.constant_trend(3)
+    c.beta = np.array([[0.1, 0.2]])            # one column per target (upstream's setter raises here)
+    assert c.beta.shape == (1, 2)
+
+
+def test_kernel_ids_and_restricted_parameter_split():
+    assert b2.resolve_corr("generalized_exponential") == _lib.CORR_GENEXP
+    gp = b2.GaussianProcess(thetaL=[1e-3] * 2, thetaU=[1e2] * 2, likelihood="restricted")                 # noisy (nugget 1e-6)
+    th, s2, nv = gp._split_par_restricted([0.5, 0.6, 0.9])
+    assert list(th) == [0.5, 0.6] and s2 == 0.9 and nv == 1e-6                                            # gpr.py:829-830
+    gp = b2.GaussianProcess(thetaL=[1e-3] * 2, thetaU=[1e2] * 2, likelihood="restricted", nugget=None)
+    assert gp._split_par_restricted([0.5, 0.6, 0.9])[2] == 0.0                                            # gpr.py:826-827
+    gp = b2.GaussianProcess(thetaL=[1e-3] * 2, thetaU=[1e2] * 2, likelihood="restricted", noise_estim=True)
+    th, s2, nv = gp._split_par_restricted([0.5, 0.6, 0.9, 0.05])
+    assert list(th) == [0.5, 0.6] and (s2, nv) == (0.9, 0.05)                                             # gpr.py:832-833
