@@ -193,6 +193,15 @@ int b200bo_acq_grad(b200bo_handle h, const double* Xc, int64_t M, int acq_id, in
  * fused tensor-core kernel alone over M host candidates (no band stage, results discarded); products = 1 or 3. */
 int b200bo_debug_fused_time(b200bo_handle h, const double* Xc_host, int64_t M, int products, int reps, double* out_ms);
 
+/* -- environment knobs read at b200bo_create (developer / A-B switches; the defaults are the measured best) --------
+ *   B200BO_FAST_KERNEL=1..5      generation of the fused tensor-core kernel (default 5), = b200bo_set_fast_kernel
+ *   B200BO_FAST_PRODUCTS=1|3     fp16 products per MAC of the first acquisition pass (default 1)
+ *   B200BO_REPLAY_MB=n           scratch budget of generation 4 (default 64)
+ *   B200BO_CHOL_LOOKAHEAD=0|1|2  Cholesky: single stream | look-ahead, separate kernels | fused panel step where faster
+ *   B200BO_GRAPHS=0|1            CUDA-graph replay of the factorisation stretches for N <= 2048 (default 1)
+ *   B200BO_WAIT_HINT_NS=n        suspend-time hint of the mbarrier waits in the fused kernels
+ *   B200BO_TRACE=path            dump a clock64 timeline of CTA 0 of the fused kernel (Matern-5/2, one product) */
+
 /* -- instrumentation ------------------------------------------------------------------------------------
  * CUDA-event timings (ms) of the last predict/acq call, recorded on the handle's stream:
  *   [0] whole call on device  [1] k* build kernels  [2] L^-1 k* contraction kernels (the dominant kernel)
