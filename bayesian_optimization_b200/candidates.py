@@ -72,6 +72,20 @@ def _feasible(x: Sequence[float], h: Optional[Callable], g: Optional[Callable]) 
     return bool(cond_h and cond_g)
 
 
+def rank_values(crit, Xc: np.ndarray) -> Tuple[np.ndarray, bool]:
+    """(values (M,), exact?) used to RANK the candidates.  A model built with precision="fast" is scored by the fused
+    tensor-core pass (posterior moments to ~1e-3, criterion evaluated on the device from them); whatever is picked
+    from that ranking is re-scored exactly afterwards, and the exact arg-max of the pass joins the picks.  Any other
+    model takes the float64 path, whose values are the reference's to 1e-7."""
+    model = getattr(crit, "_model", None)
+    eng = getattr(model, "engine", None) if getattr(model, "precision", "fp64") == "fast" else None
+    if eng is not None and hasattr(eng, "acq_from_moments") and getattr(model, "_sub", None) is None:
+        yh, ms = eng.predict(Xc, True)
+        _, _, vals = eng.acq_from_moments(yh, ms, crit._acq_id, crit.minimize, crit._plugin_value(), [crit._param()], True)
+        return np.asarray(vals)[0], False
+    return np.asarray(crit.batch(Xc, [crit._param()]))[0], True
+
+
 def refine(criterion, X0: np.ndarray, bounds: np.ndarray, steps: int = 20, step0: float = 0.05) -> Tuple[np.ndarray, np.ndarray]:
     """Projected gradient ascent on K points at once; every iteration is one device call.  Per-point step sizes
     (relative to the box), doubled after an accepted step and halved after a rejected one.  Returns the best
@@ -126,7 +140,7 @@ def argmax_candidates(
     Xc = sample_candidates(search_space, M, rng)
     if Xc.ndim != 2 or Xc.shape[1] != bounds.shape[0]:
         raise ValueError("sampled candidates do not match the bounds")
-    vals = np.asarray(crit.batch(Xc, [crit._param()]))[0]
+    vals, exact = rank_values(crit, Xc)
     vals = np.where(np.isfinite(vals), vals, -np.inf)
     K = int(min(max(refine_top, 1), M))
     if h is None and g is None:
@@ -143,7 +157,16 @@ def argmax_candidates(
         if not top:
             return [], []
         top = np.asarray(top)
-    Xk, vk = Xc[top], vals[top]
+    if not exact:
+        # tensor-core ranking: add the exact arg-max of the pass (band re-scored in float64) and re-score the picks
+        _, bi = crit.argmax(Xc)
+        if h is None and g is None and int(bi[0]) not in set(int(t) for t in top):
+            top = np.concatenate([[int(bi[0])], top])
+        Xk = Xc[top]
+        vk = np.asarray(crit.batch(Xk, [crit._param()]))[0]
+        vk = np.where(np.isfinite(vk), vk, -np.inf)
+    else:
+        Xk, vk = Xc[top], vals[top]
     if refine_steps > 0:
         Xr, vr = refine(crit, Xk, bounds, refine_steps)
         Xk, vk = np.vstack([Xr, Xk]), np.concatenate([vr, vk])

@@ -104,3 +104,22 @@ def test_ei_on_device_matches_oracle():
     Xc = cd.sample_candidates(Space([[0, 1]] * D), 20000, np.random.default_rng(3))
     yo, mo = go.predict_chunked(ora, Xc, 2048)
     assert v >= go.ei(yo, mo, ora.sigma2, pl).max() * (1 - 1e-9)
+
+
+@pytest.mark.gpu
+def test_fast_precision_ranking_matches_float64_choice():
+    """precision="fast": candidates ranked by the tensor-core pass, picks re-scored exactly -- the raw (unpolished)
+    answer must be the float64 path's arg-max"""
+    from bayesian_optimization_b200 import workloads
+
+    N, D = 600, 6
+    X, y, theta = workloads.canonical_problem(N, D)
+    res = {}
+    for prec in ("fp64", "fast"):
+        gp = b2.GaussianProcess(mean=b2.constant_trend(D), corr="matern52", thetaL=[1e-5] * D, thetaU=[1e2] * D, nugget=1e-6,
+                                precision=prec)
+        gp.fit_fixed(X, y, theta, 1.0)
+        res[prec] = b2.argmax_candidates(b2.MGFI(model=gp, t=2.0), Space([[0, 1]] * D), n_candidates=50000,
+                                         rng=np.random.default_rng(4), refine_steps=0)
+    assert res["fast"][0] == res["fp64"][0]
+    assert res["fast"][1] == pytest.approx(res["fp64"][1], rel=1e-9)
