@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libb200bo.so")
 
 # ids, kept in sync with include/b200bo.h (tests/test_abi.py parses the header and compares)
-CORR_RBF, CORR_MATERN12, CORR_MATERN32, CORR_MATERN52, CORR_ABSEXP, CORR_CUBIC, CORR_GENEXP = range(7)
+CORR_RBF, CORR_MATERN12, CORR_MATERN32, CORR_MATERN52, CORR_ABSEXP, CORR_CUBIC, CORR_GENEXP, CORR_MATERN_NU = range(8)
 MODE_NOISELESS, MODE_NOISY, MODE_NOISE_ESTIM = range(3)
 TREND_CONSTANT, TREND_LINEAR, TREND_QUADRATIC = 0, 1, 2
 FIT_OK, FIT_NOT_SPD, FIT_REJECTED = range(3)

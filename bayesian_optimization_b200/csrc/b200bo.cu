@@ -471,14 +471,15 @@ static int factor_impl(b200bo_handle h, int corr, const double* theta, int n_the
                        double* out_sigma2, double* out_noise_var, int* out_status, bool restricted) {
   CHECK_ARG(h && theta, "NULL argument");
   CHECK_ARG(h->N > 0, "set_train first");
-  CHECK_ARG(corr >= 0 && corr <= 6, "unknown correlation id");
+  CHECK_ARG(corr >= 0 && corr <= 7, "unknown correlation id");
   CHECK_ARG(mode >= 0 && mode <= 2, "unknown estimation mode");
   CHECK_ARG(trend >= B200BO_TREND_CONSTANT && trend <= B200BO_TREND_QUADRATIC, "unknown trend id");
   CHECK_ARG(trend_p(trend, h->D) <= TR_PMAX, "at most 64 trend basis functions are supported");
   CHECK_ARG(!(restricted && trend != B200BO_TREND_CONSTANT), "the restricted likelihood is implemented for the constant trend");
-  if (corr == GENEXP) {
+  if (corr_has_extra_param(corr)) {
     CHECK_ARG(n_theta == 2 || n_theta == h->D + 1, "Length of theta must be 2 or D + 1");  // kernel.py:367-370
-    --n_theta;  // the last entry is the exponent
+    --n_theta;  // the last entry is the exponent (generalized_exponential) or nu (general Matern)
+    CHECK_ARG(corr != MATERN_NU || (theta[n_theta] > 0 && theta[n_theta] <= 50.0), "nu must be in (0, 50]");
   }
   CHECK_ARG(n_theta == 1 || n_theta == h->D, "Length of theta must be 1 or D");
   CU_TRY(cudaSetDevice(h->device));
@@ -503,7 +504,7 @@ static int factor_impl(b200bo_handle h, int corr, const double* theta, int n_the
 
   std::vector<double> th(D + 1, 0.0);
   for (int d = 0; d < D; ++d) th[d] = theta[n_theta == 1 ? 0 : d];
-  if (corr == GENEXP) th[D] = theta[n_theta];
+  if (corr_has_extra_param(corr)) th[D] = theta[n_theta];
   cudaStream_t st = h->stream;
   h->evs.reset();
   PhaseTimer pt{h};
@@ -1289,7 +1290,7 @@ static int make_f16_map(CUtensorMap* map, const __half* base, int inner, int row
   return 0;
 }
 
-static bool fast_supported(const b200bo_ctx* h) { return h->corr != CUBIC && h->corr != GENEXP && h->D <= 64; }
+static bool fast_supported(const b200bo_ctx* h) { return h->corr != CUBIC && !corr_has_extra_param(h->corr) && h->D <= 64; }
 
 static int ensure_fast_state(b200bo_handle h) {
   if (h->fast_ready) return 0;
@@ -1938,7 +1939,7 @@ static int grad_common(b200bo_handle h, const double* Xc, int64_t M, int acq_id,
                        double* yhat, double* mse, double* y_dx, double* mse_dx, double* val, double* dx) {
   CHECK_ARG(h && (Xc || M == 0), "NULL argument");
   if (!h->factored) return set_err(B200BO_E_STATE, "gradient before a successful factor()");
-  CHECK_ARG(h->corr != CUBIC && h->corr != GENEXP, "this kernel has no gradient (corr_dx: `pass`, gpr.py:652-655)");
+  CHECK_ARG(h->corr != CUBIC && !corr_has_extra_param(h->corr), "this kernel has no gradient (corr_dx: `pass`, gpr.py:652-655)");
   CHECK_ARG(h->trend == B200BO_TREND_CONSTANT, "the posterior gradient is implemented for the constant trend");
   CU_TRY(cudaSetDevice(h->device));
   int rc;

@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(256) kmat_assemble_kernel(AssembleArgs p) {
     xj[e] = p.Xt[(size_t)d * p.ld + j0 + c];
   }
   for (int d = tid; d < p.D; d += 256) th[d] = p.theta[d];
-  const double pw = p.corr == GENEXP ? p.theta[p.D] : 0.0;  // generalized_exponential: the exponent follows theta
+  const double pw = corr_has_extra_param(p.corr) ? p.theta[p.D] : 0.0;  // exponent (generalized_exponential) / nu (general Matern)
   __syncthreads();
   // thread -> 4 rows x 4 cols (cols interleaved by 16 so smem reads of xj are conflict-free)
   const int tr = (tid / 16) * 4, tc = tid % 16;
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(256) kmat_assemble_kernel(AssembleArgs p) {
       } else if (gi == gj) {
         v = p.mode == 1 ? (p.sigma2 * 1.0 + p.noise_var) / s2t : (p.mode == 2 ? p.alpha * 1.0 + (1.0 - p.alpha) : 1.0);
       } else {
-        double r = corr_finish(p.corr, acc[a][b]);
+        double r = corr_finish_p(p.corr, acc[a][b], pw);
         v = p.mode == 1 ? (p.sigma2 * r) / s2t : (p.mode == 2 ? p.alpha * r : r);
       }
       tile[(tr + a) * 66 + tc + 16 * b] = v;

@@ -13,7 +13,7 @@
 
 namespace b2 {
 
-enum Corr { RBF = 0, MATERN12 = 1, MATERN32 = 2, MATERN52 = 3, ABSEXP = 4, CUBIC = 5, GENEXP = 6 };
+enum Corr { RBF = 0, MATERN12 = 1, MATERN32 = 2, MATERN52 = 3, ABSEXP = 4, CUBIC = 5, GENEXP = 6, MATERN_NU = 7 };
 enum Acq { ACQ_EI = 0, ACQ_PI = 1, ACQ_UCB = 2, ACQ_MGFI = 3 };
 
 // ---- correlation: accumulate over features, then finish -------------------------------------------
@@ -33,7 +33,89 @@ B2_HD double corr_accum(int corr, double acc, double theta, double diff) {
 // generalized_exponential carries its exponent next to theta: exp(-sum theta_j |d_j|^pw)   kernel.py:372-373
 B2_HD double corr_accum_p(int corr, double acc, double theta, double diff, double pw) {
   if (corr == GENEXP) return acc + theta * pow(fabs(diff), pw);
-  return corr_accum(corr, acc, theta, diff);
+  return corr_accum(corr, acc, theta, diff);  // MATERN_NU accumulates sum theta_j d_j^2 like the other Matern kernels
+}
+B2_HD bool corr_has_extra_param(int corr) { return corr == GENEXP || corr == MATERN_NU; }
+
+// ---- modified Bessel function of the second kind K_nu(x), real nu >= 0, x > 0 -----------------------------------
+// What the reference's general-nu Matern calls scipy.special.kv for (kernel.py:201-207).  Temme's method: with
+// nu = n + mu, |mu| <= 1/2, K_mu and K_mu+1 come from a power series (x <= 2) or from Steed's continued fraction
+// (x > 2), then the upward recurrence K_{k+1} = K_{k-1} + (2 k / x) K_k, which is stable for K.
+B2_HD double rgamma1p_odd(double mu) {
+  // Gamma1(mu) = (1/Gamma(1 - mu) - 1/Gamma(1 + mu)) / (2 mu) from the Taylor series of 1/Gamma(1 + z) (odd part)
+  const double m2 = mu * mu;
+  return -(0.5772156649015329 + m2 * (-0.0420026350340952 + m2 * (-0.0421977345555443 + m2 * (0.0072189432466630 +
+           m2 * (-0.0002152416741149 + m2 * (-0.0000201348547807 + m2 * 0.0000011330272320))))));
+}
+B2_HD void bessel_k_pair(double mu, double x, double* kmu, double* kmu1) {
+  const double PI = 3.141592653589793, EPS = 1e-17;
+  const double gampl = 1.0 / tgamma(1.0 + mu), gammi = 1.0 / tgamma(1.0 - mu);
+  if (x <= 2.0) {
+    const double b = 0.5 * x, d0 = -log(b), e0 = mu * d0;
+    const double pimu = PI * mu;
+    const double fact = fabs(pimu) < 1e-9 ? 1.0 : pimu / sin(pimu);
+    const double fact2 = fabs(e0) < 1e-9 ? 1.0 : sinh(e0) / e0;
+    const double gam1 = fabs(mu) < 0.1 ? rgamma1p_odd(mu) : (gammi - gampl) / (2.0 * mu);
+    const double gam2 = 0.5 * (gammi + gampl);
+    double ff = fact * (gam1 * cosh(e0) + gam2 * fact2 * d0);
+    double sum = ff;
+    const double ee = exp(e0);
+    double p = 0.5 * ee / gampl, q = 0.5 / (ee * gammi), c = 1.0, sum1 = p;
+    const double d = b * b;
+    for (int i = 1; i <= 500; ++i) {
+      ff = (i * ff + p + q) / ((double)i * i - mu * mu);
+      c *= d / i;
+      p /= (i - mu);
+      q /= (i + mu);
+      const double del = c * ff;
+      sum += del;
+      sum1 += c * (p - i * ff);
+      if (fabs(del) < fabs(sum) * EPS) break;
+    }
+    *kmu = sum;
+    *kmu1 = sum1 * 2.0 / x;
+  } else {
+    double b = 2.0 * (1.0 + x), d = 1.0 / b, h = d, delh = d, q1 = 0.0, q2 = 1.0;
+    const double a1 = 0.25 - mu * mu;
+    double q = a1, c = a1, a = -a1, s = 1.0 + q * delh;
+    for (int i = 2; i <= 500; ++i) {
+      a -= 2 * (i - 1);
+      c = -a * c / i;
+      const double qnew = (q1 - b * q2) / a;
+      q1 = q2;
+      q2 = qnew;
+      q += c * qnew;
+      b += 2.0;
+      d = 1.0 / (b + a * d);
+      delh = (b * d - 1.0) * delh;
+      h += delh;
+      const double dels = q * delh;
+      s += dels;
+      if (fabs(dels / s) < EPS) break;
+    }
+    h = a1 * h;
+    *kmu = sqrt(PI / (2.0 * x)) * exp(-x) / s;
+    *kmu1 = *kmu * (mu + x + 0.5 - h) / x;
+  }
+}
+B2_HD double bessel_kv(double nu, double x) {
+  const int nl = (int)(nu + 0.5);
+  const double mu = nu - nl;
+  double k0, k1;
+  bessel_k_pair(mu, x, &k0, &k1);
+  for (int i = 1; i <= nl; ++i) {  // K_{mu+i+1} = K_{mu+i-1} + 2 (mu + i) / x K_{mu+i}
+    const double kn = k0 + 2.0 * (mu + i) / x * k1;
+    k0 = k1;
+    k1 = kn;
+  }
+  return k0;
+}
+// general-nu Matern: 2^(1-nu) / Gamma(nu) t^nu K_nu(t), t = sqrt(2 nu) h, h = 0 replaced by eps   kernel.py:201-207
+B2_HD double matern_general(double h, double nu) {
+  if (h == 0.0) h = DBL_EPSILON;
+  const double t = sqrt(2.0 * nu) * h;
+  if (t > 705.0) return 0.0;  // K_nu underflows
+  return exp2(1.0 - nu) / tgamma(nu) * pow(t, nu) * bessel_kv(nu, t);
 }
 
 B2_HD double corr_finish(int corr, double acc) {
@@ -55,6 +137,11 @@ B2_HD double corr_finish(int corr, double acc) {
     default:
       return acc;  // CUBIC: the running product is the value (kernel.py:464)
   }
+}
+
+B2_HD double corr_finish_p(int corr, double acc, double pw) {
+  if (corr == MATERN_NU) return matern_general(sqrt(acc), pw);  // pw = nu
+  return corr_finish(corr, acc);
 }
 
 // ---- d r / d theta_j = corr_dtheta_factor(acc) * corr_dtheta_weight(diff_j) -------------------------------

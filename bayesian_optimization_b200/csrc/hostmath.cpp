@@ -13,5 +13,7 @@ double b2h_acq(int acq, double yhat, double mse, double sigma2, double plugin, d
   if (acq == b2::ACQ_MGFI && par > 22.36) par = 22.36;
   return b2::acq_value(acq, yhat, mse, sigma2, plugin, par, minimize);
 }
+double b2h_kv(double nu, double x) { return b2::bessel_kv(nu, x); }
+double b2h_matern(double h, double nu) { return b2::matern_general(h, nu); }
 int b2h_arg_better(double av, long long ai, double bv, long long bi) { return b2::arg_better(av, ai, bv, bi); }
 }

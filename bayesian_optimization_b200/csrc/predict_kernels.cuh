@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(256) kstar_kernel(KstarArgs p) {
     xc[e] = (m0 + r < p.M) ? p.Xc[(size_t)(m0 + r) * p.D + d] : 0.0;
   }
   for (int d = tid; d < p.D; d += 256) th[d] = p.theta[d];
-  const double pw = p.corr == GENEXP ? p.theta[p.D] : 0.0;  // generalized_exponential: the exponent follows theta
+  const double pw = corr_has_extra_param(p.corr) ? p.theta[p.D] : 0.0;  // exponent (generalized_exponential) / nu (general Matern)
   __syncthreads();
   double ysum[KS_ROWS];
 #pragma unroll
@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(256) kstar_kernel(KstarArgs p) {
     double g = p.gamma[n];
 #pragma unroll
     for (int r = 0; r < KS_ROWS; ++r) {
-      double k = n < p.N ? corr_finish(p.corr, acc[r]) : 0.0;  // padding columns contribute nothing
+      double k = n < p.N ? corr_finish_p(p.corr, acc[r], pw) : 0.0;  // padding columns contribute nothing
       if (p.Kst) p.Kst[(size_t)(m0 + r) * p.ld + n] = k;
       ysum[r] += k * g;
     }

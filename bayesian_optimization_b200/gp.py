@@ -45,10 +45,10 @@ def resolve_corr(corr) -> int:
         raise ValueError("corr should be one of %s or callable, %s was given." % (list(_CORR_IDS), corr))
     if isinstance(corr, functools.partial) and getattr(corr.func, "__name__", "") == "matern":
         nu = corr.keywords.get("nu", 1.5)
-        try:
-            return {0.5: _lib.CORR_MATERN12, 1.5: _lib.CORR_MATERN32, 2.5: _lib.CORR_MATERN52}[float(nu)]
-        except KeyError:
-            raise ValueError(f"matern nu={nu} has no device kernel (0.5, 1.5, 2.5 are available)") from None
+        if not float(nu) > 0:
+            raise ValueError(f"matern nu={nu} must be positive")
+        # 0.5 / 1.5 / 2.5 have closed forms (kernel.py:189-200); any other nu goes through K_nu (kernel.py:201-207)
+        return {0.5: _lib.CORR_MATERN12, 1.5: _lib.CORR_MATERN32, 2.5: _lib.CORR_MATERN52}.get(float(nu), _lib.CORR_MATERN_NU)
     name = getattr(corr, "__name__", None)
     if name in _CORR_IDS:
         return _CORR_IDS[name]
@@ -143,6 +143,8 @@ class GaussianProcess:
     # ---- checks (gpr.py:279-310, :1199-1248) -------------------------------------------------------
     def _check_params(self):
         self._corr_id = resolve_corr(self.corr_type)
+        # general-nu Matern: nu is an argument of the callable upstream; the device takes it as one more entry behind theta
+        self._corr_extra = float(self.corr_type.keywords["nu"]) if self._corr_id == _lib.CORR_MATERN_NU else None
         if self.thetaL is not None and self.thetaU is not None:
             if self.thetaL.size != self.thetaU.size:
                 raise ValueError("thetaL and thetaU must have the same length.")
@@ -230,13 +232,17 @@ class GaussianProcess:
             return par, 0.0
         return par[:-1], float(par[-1])
 
+    def _theta_dev(self, theta):
+        theta = np.asarray(theta, dtype=np.float64).ravel()
+        return theta if getattr(self, "_corr_extra", None) is None else np.r_[theta, self._corr_extra]
+
     def _beta_fixed(self):
         return None if self.estimate_trend else np.asarray(self.mean.beta, dtype=np.float64).ravel()
 
     def _factor(self, par):
         theta, last = self._split_par(par)
         nv = float(np.atleast_1d(self.noise_var)[0]) if self.estimation_mode == "noisy" else 0.0
-        llf, s2, nvo, status = self.engine.factor(self._corr_id, theta, _MODES[self.estimation_mode], last, nv,
+        llf, s2, nvo, status = self.engine.factor(self._corr_id, self._theta_dev(theta), _MODES[self.estimation_mode], last, nv,
                                                   self._trend_id, self._beta_fixed())
         self._cache = {}
         return llf, s2, nvo, status
@@ -273,7 +279,7 @@ class GaussianProcess:
             raise NotImplementedError("the restricted likelihood is implemented for one target")
         theta, s2, nv = self._split_par_restricted(par)
         n_par = np.size(par)
-        llf, status = self.engine.factor_restricted(self._corr_id, theta, s2, nv, self._trend_id, self._beta_fixed())
+        llf, status = self.engine.factor_restricted(self._corr_id, self._theta_dev(theta), s2, nv, self._trend_id, self._beta_fixed())
         self._cache = {}
         if status != _lib.FIT_OK:
             return (-np.inf, np.zeros((n_par, 1))) if eval_grad else -np.inf
@@ -286,7 +292,7 @@ class GaussianProcess:
 
     def _refactor(self):
         if getattr(self, "_restricted_par", None) is not None:
-            _, status = self.engine.factor_restricted(self._corr_id, self.theta_, self._restricted_par[0],
+            _, status = self.engine.factor_restricted(self._corr_id, self._theta_dev(self.theta_), self._restricted_par[0],
                                                       self._restricted_par[1], self._trend_id, self._beta_fixed())
             if status != _lib.FIT_OK:  # pragma: no cover - the same inputs factored before
                 raise RuntimeError("re-factorisation of a fitted model failed")

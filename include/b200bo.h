@@ -38,6 +38,9 @@ typedef struct b200bo_ctx* b200bo_handle;
 #define B200BO_CORR_MATERN52 3 /* matern(nu=2.5): (1+sqrt5 h+5h^2/3) exp(-sqrt5 h)  kernel.py:197-200 */
 #define B200BO_CORR_ABSEXP 4   /* "absolute_exponential": exp(-sum theta |d|)       kernel.py:247-286 */
 #define B200BO_CORR_CUBIC 5    /* "cubic": prod (1 - 3 t^2 + 2 t^3), t=min(1,theta|d|) kernel.py:419-466 */
+#define B200BO_CORR_MATERN_NU 7 /* matern(nu = anything else): 2^(1-nu)/Gamma(nu) t^nu K_nu(t), t = sqrt(2 nu) h; theta has
+                                   n+1 (or 2) entries, the last one is nu   kernel.py:201-207.  K_nu by Temme's method on
+                                   the device (scipy.special.kv upstream); float64 path only, no gradients */
 #define B200BO_CORR_GENEXP 6   /* "generalized_exponential": exp(-sum theta |d|^p); theta has n+1 (or 2) entries, the
                                   last one is p   kernel.py:332-374.  float64 path only, no gradients (as upstream) */
 

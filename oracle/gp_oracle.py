@@ -32,6 +32,7 @@ CORR_MATERN52 = 3  # matern(nu=2.5)       kernel.py:197-200
 CORR_ABSEXP = 4  # "absolute_exponential" kernel.py:247-286
 CORR_CUBIC = 5  # "cubic"                  kernel.py:419-466
 CORR_GENEXP = 6  # "generalized_exponential" kernel.py:332-374 (theta = [theta_1..n | theta, p])
+CORR_MATERN_NU = 7  # matern(nu) for any other nu: kernel.py:201-207 via scipy.special.kv (theta = [theta_1..n | theta, nu])
 
 CORR_NAMES = {
     "squared_exponential": CORR_RBF,
@@ -81,6 +82,17 @@ def corr_values(corr: int, theta: np.ndarray, d: np.ndarray) -> np.ndarray:
             raise ValueError("Length of theta must be 2 or %s" % (nf + 1))
         th = np.repeat(theta[0], nf) if theta.size == 2 and nf > 1 else theta[:-1]
         return np.exp(-np.sum(th.reshape(1, nf) * np.abs(d) ** theta[-1], axis=1))
+    if corr == CORR_MATERN_NU:  # nu rides as the last entry of theta (an argument of the callable upstream)
+        from scipy.special import gamma as _gamma, kv as _kv
+
+        if theta.size not in (2, nf + 1):
+            raise ValueError("Length of theta must be 2 or %s" % (nf + 1))
+        nu, th = float(theta[-1]), theta[:-1]
+        h = np.sqrt(th[0] * np.sum(d**2, axis=1)) if th.size == 1 else np.sqrt(np.sum(th.reshape(1, nf) * d**2, axis=1))
+        K = h.copy()
+        K[K == 0.0] += np.finfo(float).eps  # kernel.py:203
+        tmp = math.sqrt(2 * nu) * K
+        return (2 ** (1.0 - nu)) / _gamma(nu) * tmp**nu * _kv(nu, tmp)
     if theta.size not in (1, nf):
         raise ValueError("Length of theta must be 1 or %s" % nf)
     if corr == CORR_RBF:

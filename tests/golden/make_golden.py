@@ -31,12 +31,13 @@ CORR = {
     go.CORR_CUBIC: "cubic",
     go.CORR_GENEXP: "generalized_exponential",
 }
+MATERN_NU = lambda nu: functools.partial(ns.matern, nu=nu)  # noqa: E731  general nu: kernel.py:201-207
 
 
 def make_gp(corr, D, mode, ok, nugget, beta=0.0, trend=go.TREND_CONSTANT):
     tcls = {go.TREND_CONSTANT: ns.constant_trend, go.TREND_LINEAR: ns.linear_trend, go.TREND_QUADRATIC: ns.quadratic_trend}[trend]
     mean = tcls(D) if ok else tcls(D, beta=beta)
-    nt = D + 1 if corr == go.CORR_GENEXP else D
+    nt = D + 1 if corr == go.CORR_GENEXP else D  # (general-nu Matern: nu is an argument of the callable, theta stays D)
     kw = dict(mean=mean, corr=CORR[corr], thetaL=[1e-5] * nt, thetaU=[1e2] * nt)
     if mode == go.MODE_NOISELESS:
         kw.update(nugget=None)
@@ -414,9 +415,39 @@ def multi_target():
     save("multi_target.npz", cases)
 
 
+def matern_nu():
+    """matern(nu) for nu outside {0.5, 1.5, 2.5}: the scipy.special.kv branch (kernel.py:201-207), reached upstream only
+    through ``corr=functools.partial(matern, nu=...)``."""
+    rng = np.random.default_rng(71)
+    N, D, M = 140, 3, 24
+    X = rng.uniform(0, 2, (N, D))
+    y = np.cos(2 * X).sum(axis=1) + 0.2 * rng.standard_normal(N)
+    y = (y - y.mean()) / y.std()
+    Xc = rng.uniform(0, 2, (M, D))
+    Xc[:2] = X[:2]
+    theta = [0.6, 1.1, 0.3]
+    cases = {}
+    for nu in (0.8, 2.0, 3.5):
+        for mode, mn, last, nug in [(go.MODE_NOISELESS, "nl", None, None), (go.MODE_NOISY, "ny", 0.8, 1e-2),
+                                    (go.MODE_NOISE_ESTIM, "ne", 0.95, 1e-2)]:
+            if mode == go.MODE_NOISELESS and nu > 2.5:
+                continue
+            for ok in (True, False):
+                CORR[go.CORR_MATERN_NU] = MATERN_NU(nu)
+                name = f"mnu{nu}_{mn}_{'ok' if ok else 'sk'}"
+                c = run_case(X, y, Xc, go.CORR_MATERN_NU, theta, mode, ok, last, nug, beta=0.1)
+                c["nu"] = nu
+                cases[name] = c
+                print(name, c["llf"])
+    save("matern_nu.npz", cases)
+
+
 if __name__ == "__main__":
     if "--fit-only" in sys.argv:
         fit_full()
+        sys.exit(0)
+    if "--matern-nu-only" in sys.argv:
+        matern_nu()
         sys.exit(0)
     if "--multi-only" in sys.argv:
         multi_target()
@@ -442,5 +473,6 @@ if __name__ == "__main__":
     trends()
     genexp()
     multi_target()
+    matern_nu()
     if "--big" in sys.argv:
         canonical(True)

@@ -101,3 +101,22 @@ def test_argmax_ordering(hm):
         if hm.b2h_arg_better(v[i], i, best, bi):
             best, bi = v[i], i
     assert bi == int(np.argmax(v))
+
+
+def test_bessel_kv_and_general_matern_match_scipy(hm):
+    """the device's K_nu (Temme's method, gp_math.h) against scipy.special.kv, which the reference calls (kernel.py:207)"""
+    import ctypes as C
+
+    from scipy.special import gamma, kv
+
+    hm.b2h_kv.restype = C.c_double
+    hm.b2h_kv.argtypes = [C.c_double, C.c_double]
+    hm.b2h_matern.restype = C.c_double
+    hm.b2h_matern.argtypes = [C.c_double, C.c_double]
+    for nu in (0.1, 0.3, 0.8, 1.0, 1.49, 1.51, 2.0, 3.0, 3.5, 4.7, 7.25, 10.0):
+        for x in np.r_[np.logspace(-12, 0.3, 40), np.linspace(2.0001, 60, 40), 2.0]:
+            assert hm.b2h_kv(nu, float(x)) == pytest.approx(kv(nu, x), rel=5e-13), (nu, x)
+        for h in np.r_[0.0, np.logspace(-10, 1.5, 60)]:
+            hh = h if h > 0 else np.finfo(float).eps
+            t = np.sqrt(2 * nu) * hh
+            assert hm.b2h_matern(float(h), nu) == pytest.approx((2 ** (1 - nu)) / gamma(nu) * t**nu * kv(nu, t), abs=1e-13), (nu, h)
