@@ -51,8 +51,9 @@ def test_resolve_corr():
     assert b2.resolve_corr(functools.partial(matern, nu=2.5)) == _lib.CORR_MATERN52
     assert b2.resolve_corr(functools.partial(matern, nu=0.5)) == _lib.CORR_MATERN12
     assert b2.resolve_corr("absolute_exponential") == _lib.CORR_ABSEXP
+    assert b2.resolve_corr(functools.partial(matern, nu=3.5)) == _lib.CORR_MATERN_NU   # any other nu: K_nu on the device
     with pytest.raises(ValueError):
-        b2.resolve_corr(functools.partial(matern, nu=3.5))
+        b2.resolve_corr(functools.partial(matern, nu=-1.0))
     with pytest.raises(ValueError):
         b2.resolve_corr(lambda t, d: d)
 
