@@ -52,6 +52,14 @@ def test_unwraps_partials_like_base_py():
     f = Quadratic([0.0, 0.0])
     wrapped = functools.partial(functools.partial(f, return_dx=True))
     assert cd.unwrap_criterion(wrapped) is f
+    # upstream's partial_argument (utils/utils.py:163-203) decorates its closure with functools.wraps(func)
+    inner = functools.partial(f, return_dx=True)
+
+    @functools.wraps(inner)
+    def wrapper(X):
+        return inner(X)
+
+    assert cd.unwrap_criterion(wrapper) is f
     with pytest.raises(TypeError):
         cd.unwrap_criterion(lambda x: 0.0)
 
