@@ -152,3 +152,45 @@ def test_error_conventions_of_predict_and_acquisition():
     # a rejected likelihood is -inf with a zero gradient, never an exception (gpr.py:946-982): tiny total variance -> llf > 0
     llf, g = gp.log_likelihood_concentrated([1e-2] * D + [1e-5], eval_grad=True)
     assert np.isfinite(llf) or (llf == -np.inf and not np.any(g))
+
+
+MEDIUM = load_golden("medium")
+
+
+@pytest.mark.parametrize("name", ["rbf_ny_ok", "m52_ny_ok_max", "rbf_ny_ok_max", "abs_ne_sk", "rbf_ny_ok_lin"])
+def test_acquisition_classes_plumbing_vs_reference(name):
+    """EI / MGFI / UCB / EpsilonPI objects of the mirror (plug-in sign, minimise / maximise, the t cap, argmax) against
+    the reference's row-by-row values -- the arithmetic behind them is the oracle here, the device in test_parity_gpu.py"""
+    import functools
+
+    from gpu_common import CORR_ARG
+
+    c = MEDIUM[name]
+    D = c["X"].shape[1]
+    trend = {go.TREND_CONSTANT: b2.constant_trend, go.TREND_LINEAR: b2.linear_trend}[int(c["trend"])]
+    ok = bool(c["ok"])
+    mean = trend(D) if ok else trend(D, beta=np.asarray(c["beta_in"], float).ravel() if np.size(c["beta_in"]) > 1 else float(np.ravel(c["beta_in"])[0]))
+    mode = int(c["mode"])
+    kw = {go.MODE_NOISELESS: dict(nugget=None), go.MODE_NOISY: dict(nugget=float(c["nugget"])),
+          go.MODE_NOISE_ESTIM: dict(nugget=float(c["nugget"]), noise_estim=True)}[mode]
+    gp = b2.GaussianProcess(mean=mean, corr=CORR_ARG[int(c["corr"])], thetaL=[1e-5] * D, thetaU=[1e2] * D, **kw)
+    llf = gp.fit_fixed(c["X"], c["y"], c["theta"], None if mode == go.MODE_NOISELESS else float(c["par_last"]))
+    assert llf == pytest.approx(float(c["llf"]), rel=1e-11)
+    mn = bool(c["minimize"])
+    Xc = c["Xc"]
+    a = dict(rtol=1e-6, atol=1e-300)
+    ei = b2.EI(model=gp, minimize=mn)
+    assert float(ei.plugin) == pytest.approx(float(c["plugin"]), rel=1e-14)
+    np.testing.assert_allclose(ei(Xc), c["ei"], **a)
+    np.testing.assert_allclose(b2.MGFI(model=gp, minimize=mn, t=float(c["t"]))(Xc), c["mgfi"], **a)
+    np.testing.assert_allclose(b2.MGFI(model=gp, minimize=mn, t=30.0)(Xc), c["mgfi_big_t"], **a)          # t capped at 22.36
+    np.testing.assert_allclose(b2.UCB(model=gp, minimize=mn, alpha=float(c["alpha_ucb"]))(Xc), c["ucb"], rtol=1e-12)
+    np.testing.assert_allclose(b2.EpsilonPI(model=gp, minimize=mn, epsilon=float(c["eps"]))(Xc), c["epi"], **a)
+    bv, bi = b2.MGFI(model=gp, minimize=mn, t=float(c["t"])).argmax(Xc, [float(c["t"]), 30.0])
+    assert int(bi[0]) == int(np.argmax(c["mgfi"])) and int(bi[1]) == int(np.argmax(c["mgfi_big_t"]))
+    with pytest.raises(AssertionError):
+        b2.UCB(model=gp, alpha=-1.0)                                                                       # acquisition_fun.py:124
+    # the candidate-set maximiser on top (host glue end to end)
+    x, v = b2.argmax_candidates(functools.partial(ei, return_dx=False), [[-1, 2]] * D, n_candidates=2000,
+                                rng=np.random.default_rng(0), refine_steps=0 if int(c["corr"]) == go.CORR_MATERN52 else 3)
+    assert len(x) == D and v >= ei(np.array([x]))[0] * (1 - 1e-9)
