@@ -22,6 +22,7 @@
 #include "fast5_kernels.cuh"
 #include "fit_kernels.cuh"
 #include "grad_kernels.cuh"
+#include "host_qr.h"
 #include "predict_kernels.cuh"
 #include "trend_kernels.cuh"
 
@@ -765,57 +766,8 @@ static int factor_impl(b200bo_handle h, int corr, const double* theta, int n_the
     h->h_beta.assign(p, 0.0);
     h->h_G.assign((size_t)p * p, 0.0);
     if (est) {
-      // Householder QR in place on a column-major copy; the reflectors are applied to Yt as they are formed
-      std::vector<double> a((size_t)N * p), qty(yt.begin(), yt.begin() + N), tau(p, 0.0);
-      for (int c = 0; c < p; ++c)
-        for (int i = 0; i < N; ++i) a[(size_t)c * N + i] = h->h_Ft[(size_t)i * p + c];
-      for (int j = 0; j < p && j < N; ++j) {
-        double* x = &a[(size_t)j * N];
-        double xn2 = 0.0;
-        for (int i = j + 1; i < N; ++i) xn2 += x[i] * x[i];
-        const double alpha = x[j];
-        if (xn2 == 0.0) {
-          tau[j] = 0.0;
-        } else {
-          const double bt = -copysign(sqrt(alpha * alpha + xn2), alpha);
-          tau[j] = (bt - alpha) / bt;
-          const double sc_ = 1.0 / (alpha - bt);
-          for (int i = j + 1; i < N; ++i) x[i] *= sc_;
-          x[j] = bt;
-        }
-        auto apply = [&](double* col) {  // col <- (I - tau v v^T) col, v = [1, x[j+1:]]
-          double w = col[j];
-          for (int i = j + 1; i < N; ++i) w += x[i] * col[i];
-          w *= tau[j];
-          col[j] -= w;
-          for (int i = j + 1; i < N; ++i) col[i] -= w * x[i];
-        };
-        if (tau[j] != 0.0) {
-          for (int c = j + 1; c < p; ++c) apply(&a[(size_t)c * N]);
-          apply(qty.data());
-        }
-      }
-      for (int i = 0; i < p; ++i)
-        for (int c = i; c < p; ++c) h->h_G[(size_t)i * p + c] = a[(size_t)c * N + i];
-      // beta = G^-1 (Q^T Yt)[:p]                                                        gpr.py:787
-      for (int i = p - 1; i >= 0; --i) {
-        double v = qty[i];
-        for (int c = i + 1; c < p; ++c) v -= h->h_G[(size_t)i * p + c] * h->h_beta[c];
-        h->h_beta[i] = v / h->h_G[(size_t)i * p + i];
-      }
-      // rho = Yt - Q Q^T Yt = Q [0; (Q^T Yt)[p:]]                                       gpr.py:806
-      std::vector<double> r(qty);
-      for (int i = 0; i < p; ++i) r[i] = 0.0;
-      for (int j = std::min(p, N) - 1; j >= 0; --j) {
-        if (tau[j] == 0.0) continue;
-        const double* x = &a[(size_t)j * N];
-        double w = r[j];
-        for (int i = j + 1; i < N; ++i) w += x[i] * r[i];
-        w *= tau[j];
-        r[j] -= w;
-        for (int i = j + 1; i < N; ++i) r[i] -= w * x[i];
-      }
-      for (int i = 0; i < N; ++i) rho[i] = r[i];
+      // thin QR with LAPACK's Householder conventions, beta and rho from it (csrc/host_qr.h)
+      thin_qr_beta_rho(h->h_Ft.data(), yt.data(), N, p, h->h_G.data(), h->h_beta.data(), rho.data());
     } else {
       for (int c = 0; c < p; ++c) h->h_beta[c] = beta_or_null[c];
       for (int i = 0; i < N; ++i) {                                                       // gpr.py:808

@@ -120,3 +120,25 @@ def test_bessel_kv_and_general_matern_match_scipy(hm):
             hh = h if h > 0 else np.finfo(float).eps
             t = np.sqrt(2 * nu) * hh
             assert hm.b2h_matern(float(h), nu) == pytest.approx((2 ** (1 - nu)) / gamma(nu) * t**nu * kv(nu, t), abs=1e-13), (nu, h)
+
+
+def test_thin_qr_matches_scipy_sign_for_sign(hm):
+    """the host-side Householder QR of the (N, p) trend panel (csrc/host_qr.h, used by b200bo_factor for p > 1) against
+    scipy.linalg.qr(mode="economic") -- what the reference calls (gpr.py:805) -- incl. LAPACK's sign convention of R"""
+    import ctypes as C
+
+    from scipy.linalg import qr, solve_triangular
+
+    hm.b2h_thin_qr.restype = None
+    hm.b2h_thin_qr.argtypes = [C.c_void_p] * 2 + [C.c_int] * 2 + [C.c_void_p] * 3
+    rng = np.random.default_rng(3)
+    for N, p in ((50, 1), (50, 4), (200, 10), (64, 64), (300, 28)):
+        Ft = np.ascontiguousarray(rng.standard_normal((N, p)) * rng.uniform(0.1, 10, p))
+        Ft[:, 0] = np.abs(Ft[:, 0]) + 0.1 if p > 1 else -np.abs(Ft[:, 0])       # both signs of the leading pivot
+        yt = rng.standard_normal(N)
+        G, beta, rho = np.empty((p, p)), np.empty(p), np.empty(N)
+        hm.b2h_thin_qr(Ft.ctypes.data, yt.ctypes.data, N, p, G.ctypes.data, beta.ctypes.data, rho.ctypes.data)
+        Q, R = qr(Ft, mode="economic")
+        np.testing.assert_allclose(G, R, rtol=1e-11, atol=1e-12 * np.abs(R).max())
+        np.testing.assert_allclose(beta, solve_triangular(R, Q.T @ yt), rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(rho, yt - Q @ (Q.T @ yt), rtol=1e-9, atol=1e-12)
