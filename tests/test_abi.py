@@ -40,12 +40,13 @@ def test_constants_match_header():
     for k, v in defs.items():
         if hasattr(_lib, k):
             assert getattr(_lib, k) == int(v), k
-    for k in ("CORR_RBF", "CORR_MATERN52", "MODE_NOISY", "ACQ_MGFI", "STATE_R", "FIT_REJECTED", "E_NODEVICE"):
+    for k in ("CORR_RBF", "CORR_MATERN52", "CORR_GENEXP", "CORR_MATERN_NU", "MODE_NOISY", "TREND_LINEAR", "TREND_QUADRATIC",
+              "ACQ_MGFI", "STATE_R", "FIT_REJECTED", "E_NODEVICE"):
         assert k in defs and hasattr(_lib, k)
     from oracle import gp_oracle as go
 
-    for k in ("CORR_RBF", "CORR_MATERN12", "CORR_MATERN32", "CORR_MATERN52", "CORR_ABSEXP", "CORR_CUBIC",
-              "MODE_NOISELESS", "MODE_NOISY", "MODE_NOISE_ESTIM", "ACQ_EI", "ACQ_PI", "ACQ_UCB", "ACQ_MGFI"):
+    for k in ("CORR_RBF", "CORR_MATERN12", "CORR_MATERN32", "CORR_MATERN52", "CORR_ABSEXP", "CORR_CUBIC", "CORR_GENEXP",
+              "CORR_MATERN_NU", "TREND_CONSTANT", "TREND_LINEAR", "TREND_QUADRATIC", "MODE_NOISELESS", "MODE_NOISY", "MODE_NOISE_ESTIM", "ACQ_EI", "ACQ_PI", "ACQ_UCB", "ACQ_MGFI"):
         assert getattr(go, k) == int(defs[k]), k
 
 
