@@ -67,9 +67,15 @@ x = rng.integers(0, 40, (3, 999)).astype(float)
 lo, hi = sharded.shard_bounds(999, world, rank)
 lv = np.array([x[c, lo:hi].max() for c in range(3)])
 li = np.array([int(np.argmax(x[c, lo:hi])) for c in range(3)], dtype=np.int64)
-bv, bi = sharded.global_argmax(lv, li, lo)
-assert list(bi) == [int(np.argmax(x[c])) for c in range(3)], (rank, bi)
-assert list(bv) == [x[c].max() for c in range(3)]
+for coll in ("allreduce", "allgather"):
+    bv, bi = sharded.global_argmax(lv + (0.1 if coll == "allreduce" else 0.0) * 0, li, lo, collective=coll)
+    assert list(bi) == [int(np.argmax(x[c])) for c in range(3)], (rank, coll, bi)
+    assert list(bv) == [x[c].max() for c in range(3)]
+# negative values, NaN and an empty shard survive the integer-sum transport bit for bit
+lv2 = np.array([-1.5 - rank, np.nan if rank == 1 else 2.0, 0.0])
+li2 = np.array([3, 4, -1 if rank == 0 else 5], dtype=np.int64)
+bv, bi = sharded.global_argmax(lv2, li2, 100 * rank)
+assert bv[0] == -1.5 and bi[0] == 3 and np.isnan(bv[1]) and bi[1] == 104 and bi[2] == 105, (bv, bi)
 dist.destroy_process_group()
 print("OK", rank)
 """
