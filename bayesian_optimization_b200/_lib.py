@@ -21,6 +21,12 @@ HOST, DEVICE = 0, 1
 PREC_FP64, PREC_FAST = 0, 1
 STATE_L, STATE_LINV, STATE_GAMMA, STATE_YT, STATE_FT, STATE_RHO, STATE_BETA, STATE_G, STATE_R = range(9)
 N_TIMINGS = 12
+N_BAND_INFO = 32
+BAND_INFO_KEYS = (
+    "dy_model", "du_model", "ds_abs_1", "ds_rel_1", "ds_abs_3", "ds_rel_3", "ds_deterministic", "linv_row2_max", "linv_2norm",
+    "linv_fro", "linv_row1_max", "gamma_2norm", "f_2norm", "x_sqnorm_max", "sd_r", "dy_cal_1", "ds_cal_1", "dy_cal_3",
+    "ds_cal_3", "cal_err_y_1", "cal_err_s_1", "cal_err_y_3", "cal_err_s_3", "dy_used", "ds_used", "ds_abs_used", "ds_rel_used",
+    "du_used", "band_err_y", "band_err_s", "band_ratio", "widen")
 
 E_ARG, E_CUDA, E_STATE, E_NODEVICE = -1, -2, -3, -4
 
@@ -67,6 +73,8 @@ SIGNATURES = {
                                           C.c_void_p]),
     "b200bo_debug_fast_rt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_void_p]),
+    "b200bo_get_band_info": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "b200bo_debug_fast_check": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int]),
     "b200bo_get_timings": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "b200bo_get_fit_timings": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
 }
@@ -124,6 +132,7 @@ class Engine:
         self._h = h
         self.device = int(device)
         self.N = self.D = 0
+        self._torch_stream = None  # address of the torch stream the handle was last bound to (device-pointer calls)
 
     def close(self):
         if getattr(self, "_h", None):
@@ -139,6 +148,17 @@ class Engine:
     # ---- configuration ---------------------------------------------------------------------------
     def set_stream(self, cuda_stream_ptr: int):
         _check(self._lib.b200bo_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+        self._torch_stream = int(cuda_stream_ptr)
+
+    def _follow_torch_stream(self):
+        """Device-pointer calls read / write tensors that the caller's CURRENT torch stream produced or will consume:
+        run the handle on that stream, so the kernels are ordered with the caller's work (the handle's own stream is
+        non-blocking and would race with it)."""
+        import torch
+
+        s = int(torch.cuda.current_stream(self.device).cuda_stream)
+        if s != self._torch_stream:
+            self.set_stream(s)
 
     def set_precision(self, prec: int):
         _check(self._lib.b200bo_set_precision(self._h, int(prec)))
@@ -219,7 +239,10 @@ class Engine:
 
     def predict_device(self, Xc, yhat, mse=None):
         """torch CUDA float64 tensors in/out (Xc (M,D) contiguous)."""
+        if Xc.ndim != 2 or Xc.shape[1] != self.D:
+            raise ValueError("Xc must be (M, D)")
         M = int(Xc.shape[0])
+        self._follow_torch_stream()
         _check(self._lib.b200bo_predict(self._h, _ptr(Xc), M, DEVICE, int(mse is not None), _ptr(yhat), _ptr(mse)))
 
     def acq(self, Xc, acq_id: int, minimize: bool, plugin: float, params, return_values: bool = False,
@@ -238,6 +261,7 @@ class Engine:
         vals = None
         if on_dev:
             vals = device_vals
+            self._follow_torch_stream()
         elif return_values:
             vals = np.empty((q, M))
         _check(self._lib.b200bo_acq(self._h, _ptr(Xc), M, DEVICE if on_dev else HOST, int(acq_id), int(bool(minimize)),
@@ -273,6 +297,8 @@ class Engine:
     def gradient(self, Xc: np.ndarray):
         """(yhat (M,), mse (M,), y_dx (M, D), mse_dx (M, D)) -- gpr.py:537-576 for every row of Xc"""
         Xc = _f64(Xc)
+        if Xc.ndim != 2 or Xc.shape[1] != self.D:
+            raise ValueError("Xc must be (M, D)")
         M, D = Xc.shape
         yh, ms = np.empty(M), np.empty(M)
         ydx, mdx = np.empty((M, D)), np.empty((M, D))
@@ -283,6 +309,8 @@ class Engine:
     def acq_grad(self, Xc: np.ndarray, acq_id: int, minimize: bool, plugin: float, param: float):
         """(value (M,), dx (M, D)) of one acquisition function -- its return_dx=True path for every row of Xc"""
         Xc = _f64(Xc)
+        if Xc.ndim != 2 or Xc.shape[1] != self.D:
+            raise ValueError("Xc must be (M, D)")
         M, D = Xc.shape
         val, dx = np.empty(M), np.empty((M, D))
         _check(self._lib.b200bo_acq_grad(self._h, Xc.ctypes.data, M, int(acq_id), int(bool(minimize)), float(plugin),
@@ -295,6 +323,19 @@ class Engine:
         out = C.c_double(0.0)
         _check(self._lib.b200bo_debug_fused_time(self._h, Xc.ctypes.data, Xc.shape[0], int(products), int(reps), C.byref(out)))
         return out.value
+
+    def band_info(self) -> dict:
+        """half-widths of the arg-max band of the tensor-core path: a-priori model, calibration, last pass (b200bo.h)"""
+        t = np.zeros(N_BAND_INFO)
+        _check(self._lib.b200bo_get_band_info(self._h, t.ctypes.data, N_BAND_INFO))
+        return dict(zip(BAND_INFO_KEYS, t.tolist()))
+
+    def fast_check(self, stride: int = 100, max_samples: int = 1 << 20) -> dict:
+        """float64 check of every stride-th candidate of the last tensor-core call (developer / bench hook)"""
+        t = np.zeros(8)
+        _check(self._lib.b200bo_debug_fast_check(self._h, int(stride), int(max_samples), t.ctypes.data, 8))
+        return dict(zip(("checked", "max_err_yhat", "max_err_mse", "max_ratio_to_allowed", "dy", "ds_cal", "ds_model_at_ss1",
+                         "products"), t.tolist()))
 
     def timings(self) -> np.ndarray:
         t = np.zeros(N_TIMINGS)

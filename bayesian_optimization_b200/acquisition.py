@@ -51,6 +51,9 @@ class AcquisitionFunction(ABC):
         return 0.0
 
     def _engine(self):
+        if getattr(self._model, "_sub", None):
+            # a k > 1 model holds one device model per target; a scalar criterion over it would silently score target 0
+            raise NotImplementedError("acquisition functions take a single-target model (y of shape (N,) or (N, 1))")
         eng = getattr(self._model, "engine", None)
         if eng is None:
             raise TypeError("the model has no B200 engine; use bayesian_optimization_b200.GaussianProcess")

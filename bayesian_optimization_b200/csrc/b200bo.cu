@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "../../include/b200bo.h"
+#include "band_kernels.cuh"
 #include "dgemm.cuh"
 #include "fast_kernels.cuh"
 #include "fast2_kernels.cuh"
@@ -112,6 +113,19 @@ using GemmTN = GemmCore<64, 64, 32, 32, true, true, 3>;    // A (KxM), B (KxN)
 
 }  // namespace
 
+struct FastModel {  // a-priori rounding model of the tensor-core pass (build_fast_model)
+  double a_max = 0, s2 = 0, fro = 0, l1_max = 0, gamma_l2 = 0, f_l2 = 0, b_max = 0, sd_r = 0;
+  double dy = 0, du = 0;                 // half-widths of yhat and of u = (Ft^T rt - 1) / G
+  double ds_abs[2] = {0, 0}, ds_rel[2] = {0, 0};  // mse: ds_abs + ds_rel sqrt(sum rt^2); [0] one product, [1] three
+  double det_ds = 0;                     // deterministic worst case (reported only)
+};
+struct LastFast {  // the candidate set of the last tensor-core pass (b200bo_debug_fast_check)
+  const double* xdev = nullptr;
+  int64_t M = 0;
+  int nprod = 0;
+};
+static const size_t PIN_BYTES = 32 * 1024;
+
 struct b200bo_ctx {
   int device = 0, num_sms = 148;
   cudaStream_t stream = nullptr;
@@ -184,6 +198,21 @@ struct b200bo_ctx {
   EvPool evs;
   double timings[B200BO_N_TIMINGS] = {0};
   double fit_timings[B200BO_N_TIMINGS] = {0};
+  bool gemm_attr[4] = {false, false, false, false};  // MaxDynamicSharedMemorySize set on this handle's device
+  bool contract_attr = false;
+  // band stage of the tensor-core path: a-priori error model, device pipeline workspaces, pinned staging
+  FastModel model;
+  bool use_model = true;          // B200BO_BAND_MODEL=0: calibrated half-widths only (round-1 behaviour, A/B runs)
+  double widen[2] = {1.0, 1.0};   // widening factor of the half-widths for this fit (x4 whenever the band shows larger errors)
+  double cal_err_y[2] = {0, 0}, cal_err_s[2] = {0, 0};  // largest errors of the calibration sample
+  double last_err_y = 0, last_err_s = 0, last_ratio = 0;
+  fk::BandArgs last_band{};
+  LastFast last_fast;
+  int dev_chunk_tiles = 0;        // B200BO_DEV_CHUNK_TILES: fused launches of this many tiles per SM on device-resident input
+  std::vector<double> Xhost;      // training set as given (N, D): the distance-error bound needs max_j ||x_j||^2 per theta
+  DevBuf<double> Xall, f_mse, bd_kst, bd_ypart, bd_part, pm_v, pm_t, pm_t2, rowsq, rowl1;
+  DevBuf<bd::BandCtl> bd_ctl;
+  uint8_t* pin = nullptr;         // pinned host staging of the band pipeline (parameters in, control block + bests out)
 };
 
 namespace {
@@ -191,7 +220,8 @@ namespace {
 template <typename Core, bool A_KM, bool B_KN>
 cudaError_t launch_gemm_on(b200bo_ctx* h, cudaStream_t st, const GemmArgs& g, int M, int N, int batch) {
   auto kern = dgemm_kernel<64, 64, 32, 32, A_KM, B_KN, 3>;
-  static bool attr_set = false;
+  // the attribute is per DEVICE: remember it per handle (one handle = one device), not per process
+  bool& attr_set = h->gemm_attr[(A_KM ? 2 : 0) + (B_KN ? 1 : 0)];
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Core::SMEM_BYTES);
     if (e != cudaSuccess) return e;
@@ -341,6 +371,8 @@ int b200bo_create(int device, b200bo_handle* out) {
   if (const char* e = getenv("B200BO_CHOL_LOOKAHEAD")) h->lookahead = std::max(0, std::min(2, atoi(e)));
   if (const char* e = getenv("B200BO_GRAPHS")) h->use_graphs = atoi(e) != 0;
   if (const char* e = getenv("B200BO_REPLAY_MB")) h->replay_mb = std::max(0, std::min(4096, atoi(e)));
+  if (const char* e = getenv("B200BO_BAND_MODEL")) h->use_model = atoi(e) != 0;
+  if (const char* e = getenv("B200BO_DEV_CHUNK_TILES")) h->dev_chunk_tiles = std::max(0, atoi(e));
   if (const char* e = getenv("B200BO_WAIT_HINT_NS")) {
     unsigned v = (unsigned)atoi(e);
     CU_TRY(cudaMemcpyToSymbol(fk::g_wait_hint_ns, &v, sizeof v));
@@ -366,6 +398,9 @@ int b200bo_destroy(b200bo_handle h) {
   h->stage[0].release(); h->stage[1].release(); h->Xband.release(); h->band_hiB.release();
   h->trace.release(); h->errout.release(); h->band_list.release(); h->band_list0.release(); h->thr_key.release();
   h->band_count.release(); h->err_flag.release();
+  h->Xall.release(); h->f_mse.release(); h->bd_kst.release(); h->bd_ypart.release(); h->bd_part.release();
+  h->pm_v.release(); h->pm_t.release(); h->pm_t2.release(); h->rowsq.release(); h->rowl1.release(); h->bd_ctl.release();
+  if (h->pin) cudaFreeHost(h->pin);
   for (int i = 0; i < 2; ++i) {
     if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
     if (h->ev_used[i]) cudaEventDestroy(h->ev_used[i]);
@@ -445,6 +480,7 @@ int b200bo_set_train(b200bo_handle h, const double* X, const double* y, int N, i
   h->factored = false;
   const int ld = h->ld;
   std::vector<double> xt((size_t)D * ld, 0.0), yy(ld, 0.0), ff(ld, 0.0);
+  h->Xhost.assign(X, X + (size_t)N * D);
   h->xmean.assign(D, 0.0);
   for (int i = 0; i < N; ++i)
     for (int d = 0; d < D; ++d) h->xmean[d] += X[(size_t)i * D + d];
@@ -483,6 +519,9 @@ static int factor_impl(b200bo_handle h, int corr, const double* theta, int n_the
     CHECK_ARG(corr != MATERN_NU || (theta[n_theta] > 0 && theta[n_theta] <= 50.0), "nu must be in (0, 50]");
   }
   CHECK_ARG(n_theta == 1 || n_theta == h->D, "Length of theta must be 1 or D");
+  // an estimated trend needs N >= p rows for the thin QR of the (N, p) panel (gpr.py:298-309 raises upstream)
+  CHECK_ARG(beta_or_null != nullptr || trend_p(trend, h->D) <= h->N,
+            "Ordinary least squares problem is undetermined: n_samples must be >= the trend basis size p");
   CU_TRY(cudaSetDevice(h->device));
   const int N = h->N, D = h->D, ld = h->ld, nb = ld / NB;
   const size_t nn = (size_t)ld * ld;
@@ -491,6 +530,8 @@ static int factor_impl(b200bo_handle h, int corr, const double* theta, int n_the
   h->fvec_ready = false;
   h->calibrated[0] = h->calibrated[1] = false;
   h->escalate = false;
+  h->widen[0] = h->widen[1] = 1.0;
+  h->last_fast = LastFast();
   CU_TRY(h->A.reserve(nn));
   CU_TRY(h->W.reserve(nn));
   CU_TRY(h->S.reserve(nn));
@@ -1030,10 +1071,9 @@ static int fp64_moments(b200bo_handle h, const double* xc_dev, int m, double* yh
   cudaStream_t st = h->stream;
   const int D = h->D, ld = h->ld;
   const int mpad = round_up(m, PC_BM);
-  static bool attr_done = false;
-  if (!attr_done) {
+  if (!h->contract_attr) {  // per handle: the attribute belongs to the handle's device
     CU_TRY(cudaFuncSetAttribute(contract_fp64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PredCore::SMEM_BYTES));
-    attr_done = true;
+    h->contract_attr = true;
   }
   const size_t ks_smem = ((size_t)KS_ROWS * D + D) * sizeof(double);
   if (ks_smem > 48 * 1024)
@@ -1242,6 +1282,9 @@ static int make_f16_map(CUtensorMap* map, const __half* base, int inner, int row
   return 0;
 }
 
+static void build_fast_model(b200bo_ctx* h, const std::vector<double>& rowsq, const std::vector<double>& rowl1,
+                             double s2_sq, double gamma_l2, double f_l2, double b_max);
+
 static bool fast_supported(const b200bo_ctx* h) { return h->corr != CUBIC && !corr_has_extra_param(h->corr) && h->D <= 64; }
 
 static int ensure_fast_state(b200bo_handle h) {
@@ -1336,6 +1379,49 @@ static int ensure_fast_state(b200bo_handle h) {
   }
   CU_TRY(h->err_flag.reserve(1));
   CU_TRY(cudaMemsetAsync(h->err_flag.p, 0, sizeof(int), st));
+  {
+    // ---- statistics of L^-1, gamma, f for the a-priori error model of the pass (build_fast_model) ----------------
+    CU_TRY(h->rowsq.reserve(ld));
+    CU_TRY(h->rowl1.reserve(ld));
+    CU_TRY(h->pm_v.reserve(ld));
+    CU_TRY(h->pm_t.reserve(ld));
+    CU_TRY(h->pm_t2.reserve(ld));
+    bd::linv_rowstats_kernel<<<(ld + 7) / 8, 256, 0, st>>>(h->W.p, ld, ld, h->rowsq.p, h->rowl1.p);
+    CU_TRY(cudaGetLastError());
+    // ||L^-1||_2^2 = largest eigenvalue of W^T W: power iteration, unnormalised (||W||_2 >= 1 because R has a unit
+    // diagonal, so the iterates cannot underflow; ten steps stay far below the double range for any R that factored)
+    const int PM_ITERS = 10;
+    bd::pm_init_kernel<<<(ld + 255) / 256, 256, 0, st>>>(h->pm_v.p, h->N, ld);
+    CU_TRY(cudaGetLastError());
+    for (int it = 0; it < PM_ITERS; ++it) {
+      if (it == PM_ITERS - 1) bd::sumsq_kernel<<<1, 1024, 0, st>>>(h->pm_v.p, ld, h->errout.p, 0);
+      tri_gemv2_kernel<<<(ld + 7) / 8, 256, 0, st>>>(h->W.p, ld, ld, h->pm_v.p, h->pm_v.p, h->pm_t.p, h->pm_t2.p);
+      tri_gemvT_partial_kernel<<<dim3((ld + 255) / 256, gchunks), 256, 0, st>>>(h->W.p, ld, ld, h->pm_t.p, h->part.p, 256);
+      colsum_partials_kernel<<<(ld + 255) / 256, 256, 0, st>>>(h->part.p, ld, gchunks, h->pm_v.p);
+    }
+    bd::sumsq_kernel<<<1, 1024, 0, st>>>(h->pm_v.p, ld, h->errout.p, 1);
+    bd::sumsq_kernel<<<1, 1024, 0, st>>>(h->gamma.p, ld, h->errout.p, 2);
+    bd::sumsq_kernel<<<1, 1024, 0, st>>>(h->fvec.p, ld, h->errout.p, 3);
+    CU_TRY(cudaGetLastError());
+    std::vector<double> rsq(ld), rl1(ld);
+    double e4[4];
+    CU_TRY(cudaMemcpyAsync(rsq.data(), h->rowsq.p, (size_t)ld * 8, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(rl1.data(), h->rowl1.p, (size_t)ld * 8, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(e4, h->errout.p, sizeof e4, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    double s2_sq = (e4[0] > 0 && std::isfinite(e4[0]) && std::isfinite(e4[1])) ? sqrt(e4[1] / e4[0]) : INFINITY;
+    // largest squared norm of a centred training point in the kernel's units (cs folds theta and the kernel's constant)
+    double b_max = 0.0;
+    for (int i = 0; i < h->N; ++i) {
+      double b = 0.0;
+      for (int d = 0; d < D; ++d) {
+        const double v = (h->Xhost[(size_t)i * D + d] - h->xmean[d]) * cs[d];
+        b += h->corr == ABSEXP ? fabs(v) : v * v;
+      }
+      b_max = std::max(b_max, b);
+    }
+    build_fast_model(h, rsq, rl1, s2_sq, sqrt(e4[2]), sqrt(e4[3]), b_max);
+  }
   if (!h->copy_stream) {
     CU_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 2; ++i) {
@@ -1493,7 +1579,63 @@ static int check_fast_err(b200bo_handle h) {
   return 0;
 }
 
-// max |fast - exact| over n band (or leading) candidates; exact moments are in (h->yhat, h->sumsq, h->dotf)
+static const int FAST_CHUNK_TILES = 8;        // candidate tiles per SM per fused launch when streaming from the host
+static const int RESCORE_DIRECT_MAX = 2048;   // widest one-product band that goes straight to the fp64 re-score
+static const int LIST0_CAP = 1 << 16;         // scan survivors (~ subsample stride x q when the criterion is not flat)
+static const int THR_STRIDE = 32;
+static const double MODEL_LAMBDA = 8.0;       // the a-priori half-widths sit MODEL_LAMBDA modelled standard deviations out
+
+// ---- a-priori rounding model of the tensor-core pass ------------------------------------------
+// The fp16 roundings of the operands are modelled as independent, mean-zero, uniform within their unit round-off (the
+// probabilistic rounding model of Higham & Mary 2019); the error of sum rt^2 is then a sum of ~N^2 such terms:
+//   sd(d ss)  <=  2 u sqrt(ss) sqrt(a_max^2 + ||L^-1||_2^2) r_max        (L^-1 part: row norms; r part: through R^-1 r)
+//   E(d ss)   <=  2 u^2 ||L^-1||_F^2 r_max^2                              (second-order term: E sum (d rt)^2)
+// with u^2 = 2 (2^-11)^2 / 3 for one fp16 product per MAC and u = 2^-21 for the split-fp16 three-product form, plus
+// the fp32 accumulation in TMEM (N products per output against partial sums bounded by the row 1-norms).  yhat and
+// Ft^T rt are dot products of the fp32 r: their half-widths come from the fp32 distance / MUFU error per element.
+// The deterministic worst-case bound (every rounding at its maximum, all aligned) is kept for the record only: it is
+// 2-3 orders of magnitude above any error the pass can produce and would put every candidate in the band.
+static void build_fast_model(b200bo_ctx* h, const std::vector<double>& rowsq, const std::vector<double>& rowl1,
+                             double s2_sq, double gamma_l2, double f_l2, double b_max) {
+  FastModel& m = h->model;
+  const int N = h->N;
+  double amax2 = 0, fro2 = 0, l1max = 0, l1sq = 0;
+  for (int i = 0; i < N; ++i) {
+    amax2 = std::max(amax2, rowsq[i]);
+    fro2 += rowsq[i];
+    l1max = std::max(l1max, rowl1[i]);
+    l1sq += rowl1[i] * rowl1[i];
+  }
+  // ||L^-1||_2^2 lies between the largest squared row norm and the squared Frobenius norm; the power iteration
+  // approaches it from below: 25 % on top, clamped into the rigorous interval
+  s2_sq = std::min(std::max(1.25 * s2_sq, amax2), fro2);
+  m.a_max = sqrt(amax2); m.s2 = sqrt(s2_sq); m.fro = sqrt(fro2); m.l1_max = l1max;
+  m.gamma_l2 = gamma_l2; m.f_l2 = f_l2; m.b_max = b_max;
+  // per-element error of the fp32 cross-correlation: slope of the kernel in its argument x error of the fp32 squared
+  // distance (three split-fp16 Gram products + fp32 adds: ~2^-21 of a_m + b_j as one standard deviation; the product
+  // |phi'(acc)| (a_m + b_j) is bounded over all candidates by K_phi max(5 b_max, 8): far candidates have r ~ 0)
+  const double e_acc = ldexp(1.0, -21) * std::max(5.0 * b_max, 8.0);
+  double kphi = 0.6931471805599453;                       // RBF / abs-exp: d 2^-acc / d acc
+  if (h->corr == MATERN32) kphi = 0.5;
+  if (h->corr == MATERN52) kphi = 1.0 / 6.0;
+  double sd_r = kphi * e_acc + ldexp(1.0, -22);            // + ex2.approx / sqrt.approx / fp32 polynomial
+  if (h->corr == MATERN12) sd_r = sqrt(e_acc) + ldexp(1.0, -22);  // exp(-sqrt(acc)): the cusp at acc = 0
+  m.sd_r = sd_r;
+  const double acc32 = ldexp(1.0, -24);
+  m.dy = MODEL_LAMBDA * (sd_r + 4.0 * acc32) * gamma_l2 + 1e-13;
+  m.du = h->estimate_trend ? MODEL_LAMBDA * (sd_r + 4.0 * acc32) * f_l2 / fabs(h->G) : 0.0;
+  for (int k = 0; k < 2; ++k) {
+    const int nprod = k == 0 ? 1 : 3;
+    const double u = k == 0 ? ldexp(1.0, -11) * sqrt(2.0 / 3.0) : ldexp(1.0, -21);
+    const double sd_op = 2.0 * u * sqrt(amax2 + s2_sq);
+    const double sd_acc = 2.0 * sqrt((double)nprod * N) * acc32 * l1max;
+    m.ds_rel[k] = MODEL_LAMBDA * sqrt(sd_op * sd_op + sd_acc * sd_acc) * h->sigma2;
+    m.ds_abs[k] = (2.0 * u * u * fro2 + ldexp(1.0, -21)) * h->sigma2 + 1e-13 * h->sigma2;
+  }
+  m.det_ds = 2.0 * ldexp(1.0, -10) * sqrt(2.0) * sqrt(l1sq) * h->sigma2;
+}
+
+// fast vs fp64 moments on n candidates whose exact moments are in (h->yhat, h->sumsq, h->dotf): calibration only
 static int fast_errors(b200bo_handle h, const long long* list_dev, long long idx_base, int n, double* ey, double* es) {
   fk::band_err_kernel<<<1, 256, 0, h->stream>>>(h->f_yhat.p, h->f_sumsq.p, h->f_dotf.p, h->yhat.p, h->sumsq.p,
                                                  h->dotf.p, list_dev, idx_base, n, h->estimate_trend, h->G,
@@ -1507,8 +1649,64 @@ static int fast_errors(b200bo_handle h, const long long* list_dev, long long idx
   return 0;
 }
 
-static const int FAST_CHUNK_TILES = 8;        // candidate tiles per SM per fused launch when streaming from the host
-static const int RESCORE_DIRECT_MAX = 2048;   // widest one-product band that goes straight to the fp64 re-score
+// phase I: the fused tensor-core pass over all candidates.  Host candidates are copied chunk by chunk into ONE device
+// buffer (copies on their own stream, overlapping the fused launches), so that the band stage gathers its rows on the
+// device.  *xdev = device address of the whole candidate set.
+static int fast_pass(b200bo_handle h, const double* Xc, int64_t M, bool dev, int nprod, const double** xdev, int* launches) {
+  cudaStream_t st = h->stream;
+  const int D = h->D;
+  int rc;
+  *launches = 0;
+  if (dev) {
+    *xdev = Xc;
+    const int64_t chunk = h->dev_chunk_tiles > 0 ? (int64_t)h->num_sms * fk::BM * h->dev_chunk_tiles : M;
+    for (int64_t a = 0; a < M; a += chunk) {
+      if ((rc = launch_fused(h, Xc + (size_t)a * D, std::min<int64_t>(chunk, M - a), (size_t)a, nprod))) return rc;
+      ++*launches;
+    }
+    return 0;
+  }
+  CU_TRY(h->Xall.reserve((size_t)M * D));
+  *xdev = h->Xall.p;
+  const int64_t FMc = (int64_t)h->num_sms * fk::BM * FAST_CHUNK_TILES;
+  // the buffer may still be read by earlier work of the compute stream
+  CU_TRY(cudaEventRecord(h->ev_used[0], st));
+  CU_TRY(cudaStreamWaitEvent(h->copy_stream, h->ev_used[0], 0));
+  int64_t i = 0;
+  for (int64_t a = 0; a < M; a += FMc, ++i) {
+    const int64_t m = std::min<int64_t>(FMc, M - a);
+    const int b = (int)(i & 1);
+    CU_TRY(cudaMemcpyAsync(h->Xall.p + (size_t)a * D, Xc + (size_t)a * D, (size_t)m * D * 8, cudaMemcpyHostToDevice, h->copy_stream));
+    CU_TRY(cudaEventRecord(h->ev_copied[b], h->copy_stream));
+    CU_TRY(cudaStreamWaitEvent(st, h->ev_copied[b], 0));
+    if ((rc = launch_fused(h, h->Xall.p + (size_t)a * D, m, (size_t)a, nprod))) return rc;
+    ++*launches;
+  }
+  return 0;
+}
+
+// once per factorisation and product count: fast vs fp64 moments on a strided sample of the candidate set
+static int calibrate_fast(b200bo_handle h, const double* xdev, int64_t M, int ci, LaunchCount* lc) {
+  cudaStream_t st = h->stream;
+  const int n = (int)std::min<int64_t>(M, std::min(h->Mc, 2048));
+  const int64_t stride = std::max<int64_t>(1, M / n);
+  CU_TRY(h->band_list.reserve(LIST0_CAP));
+  CU_TRY(h->Xband.reserve((size_t)h->Mc * h->D));
+  fk::iota_stride_kernel<<<(n + 255) / 256, 256, 0, st>>>(h->band_list.p, n, stride);
+  CU_TRY(cudaGetLastError());
+  fk::band_gather_kernel<<<(n * h->D + 255) / 256, 256, 0, st>>>(xdev, h->band_list.p, n, 0, h->D, h->Xband.p);
+  CU_TRY(cudaGetLastError());
+  int rc;
+  if ((rc = fp64_moments(h, h->Xband.p, n, h->yhat.p, 1, nullptr, lc))) return rc;
+  double ey, es;
+  if ((rc = fast_errors(h, h->band_list.p, 0, n, &ey, &es))) return rc;
+  h->cal_err_y[ci] = ey;
+  h->cal_err_s[ci] = es;
+  h->dy_cal[ci] = 8.0 * ey + 1e-13;
+  h->ds_cal[ci] = 8.0 * es + 1e-13 * h->sigma2;
+  h->calibrated[ci] = true;
+  return 0;
+}
 
 static int run_candidates_fast(b200bo_handle h, const double* Xc, int64_t M, int loc, int eval_mse, double* yhat_out,
                                double* mse_out, int acq_id, int minimize, double plugin, const double* params, int q,
@@ -1524,50 +1722,27 @@ static int run_candidates_fast(b200bo_handle h, const double* Xc, int64_t M, int
   const int ci = nprod == 1 ? 0 : 1;
   if ((rc = ensure_predict_ws(h, q, false))) return rc;
   cudaStream_t st = h->stream;
-  const int D = h->D, Mc = h->Mc;
-  const size_t Mpad = (size_t)round_up((int)std::min<int64_t>(M, INT32_MAX - 256), fk::BM);
+  const int D = h->D, Mc = h->Mc, ld = h->ld;
   CHECK_ARG(M < INT32_MAX - 256, "M too large for one call");
+  const size_t Mpad = (size_t)round_up((int)M, fk::BM);
   CU_TRY(h->f_yhat.reserve(Mpad + fk::BM));
   CU_TRY(h->f_sumsq.reserve(Mpad + fk::BM));
   CU_TRY(h->f_dotf.reserve(Mpad + fk::BM));
-  if (h->want_dbg_w) CU_TRY(h->dbg_w.reserve(Mpad * (size_t)h->ld));
+  if (h->want_dbg_w) CU_TRY(h->dbg_w.reserve(Mpad * (size_t)ld));
   h->evs.reset();
   PhaseTimer pt{h};
   LaunchCount lc;
   int fused_launches = 0;
-  if (do_acq && (rc = upload_params_reset_best(h, params, q))) return rc;
   cudaEvent_t e0 = h->evs.get(), e1 = h->evs.get();
   CU_TRY(cudaEventRecord(e0, st));
 
-  // ---- phase I: the fused tensor-core pass over all candidates ---------------------------------------
+  // ---- phase I -----------------------------------------------------------------------------------------
   pt.begin(1);
-  if (dev) {
-    if ((rc = launch_fused(h, Xc, M, 0, nprod))) return rc;
-    ++fused_launches;
-  } else {
-    // stream the host candidates through two staging buffers; copies run on their own stream
-    const int64_t FMc = (int64_t)h->num_sms * fk::BM * FAST_CHUNK_TILES;
-    for (int i = 0; i < 2; ++i) CU_TRY(h->stage[i].reserve((size_t)std::min<int64_t>(FMc, M) * D));
-    int64_t i = 0;
-    for (int64_t a = 0; a < M; a += FMc, ++i) {
-      const int64_t m = std::min<int64_t>(FMc, M - a);
-      const int b = (int)(i & 1);
-      if (i >= 2) CU_TRY(cudaStreamWaitEvent(h->copy_stream, h->ev_used[b], 0));
-      else if (i == 0) {
-        // order the first copy after whatever the compute stream did before (set_train / factor)
-        CU_TRY(cudaEventRecord(h->ev_used[0], st));
-        CU_TRY(cudaStreamWaitEvent(h->copy_stream, h->ev_used[0], 0));
-      }
-      CU_TRY(cudaMemcpyAsync(h->stage[b].p, Xc + (size_t)a * D, (size_t)m * D * 8, cudaMemcpyHostToDevice, h->copy_stream));
-      CU_TRY(cudaEventRecord(h->ev_copied[b], h->copy_stream));
-      CU_TRY(cudaStreamWaitEvent(st, h->ev_copied[b], 0));
-      if ((rc = launch_fused(h, h->stage[b].p, m, (size_t)a, nprod))) return rc;
-      CU_TRY(cudaEventRecord(h->ev_used[b], st));
-      ++fused_launches;
-    }
-  }
+  const double* xdev = nullptr;
+  if ((rc = fast_pass(h, Xc, M, dev, nprod, &xdev, &fused_launches))) return rc;
   pt.end(1);
   lc.all += fused_launches;
+  h->last_fast = {xdev, M, nprod};
 
   if (!do_acq) {
     // predict(): moments of the fast pass, MSE elementwise (approximate; see include/b200bo.h)
@@ -1576,8 +1751,9 @@ static int run_candidates_fast(b200bo_handle h, const double* Xc, int64_t M, int
     g.M = (int)M; g.estimate_trend = h->estimate_trend; g.sigma2 = h->sigma2; g.G = h->G;
     double* mo = nullptr;
     if (eval_mse) {
+      // host output: the MSE goes to its own device buffer (the fast sums stay intact for b200bo_debug_fast_check)
       if (dev) mo = mse_out;
-      else { CU_TRY(h->f_sumsq.reserve(Mpad + fk::BM)); mo = h->f_sumsq.p; }  // overwrite in place, then copy out
+      else { CU_TRY(h->f_mse.reserve(Mpad + fk::BM)); mo = h->f_mse.p; }
       g.mse_out = mo;
       mse_kernel<<<std::min(h->num_sms * 4, (int)((M + 255) / 256)), 256, 0, st>>>(g);
       CU_TRY(cudaGetLastError());
@@ -1592,56 +1768,61 @@ static int run_candidates_fast(b200bo_handle h, const double* Xc, int64_t M, int
     cudaEventElapsedTime(&ms, e0, e1);
     h->timings[0] = ms; h->timings[1] = 0; h->timings[2] = pt.total(1); h->timings[3] = 0;
     h->timings[4] = fused_launches; h->timings[5] = lc.all; h->timings[6] = 0; h->timings[7] = 0;
+    h->timings[8] = 3;
     return 0;
   }
-  if ((rc = check_fast_err(h))) return rc;
 
-  // ---- calibration of the error half-widths (once per factor()): fast vs fp64 on the leading candidates -
+  // ---- calibration (once per factor()): observed errors on a strided sample of this candidate set ------------
   pt.begin(2);
-  auto host_rows_to = [&](double* dst_dev, const long long* idx, int n) -> int {  // gather host rows, upload
-    std::vector<double> tmp((size_t)n * D);
-    for (int b = 0; b < n; ++b) memcpy(&tmp[(size_t)b * D], Xc + (size_t)idx[b] * D, (size_t)D * 8);
-    CU_TRY(cudaMemcpyAsync(dst_dev, tmp.data(), tmp.size() * 8, cudaMemcpyHostToDevice, st));
-    CU_TRY(cudaStreamSynchronize(st));
-    return 0;
-  };
   if (!h->calibrated[ci]) {
-    const int n = (int)std::min<int64_t>(M, std::min(Mc, 2048));
-    const double* xc = Xc;
-    if (!dev) {
-      CU_TRY(cudaMemcpyAsync(h->Xc.p, Xc, (size_t)n * D * 8, cudaMemcpyHostToDevice, st));
-      xc = h->Xc.p;
-    }
-    if ((rc = fp64_moments(h, xc, n, h->yhat.p, 1, nullptr, &lc))) return rc;
-    double ey, es;
-    if ((rc = fast_errors(h, nullptr, 0, n, &ey, &es))) return rc;
-    h->dy_cal[ci] = 8.0 * ey + 1e-13;
-    h->ds_cal[ci] = 8.0 * es + 1e-13 * h->sigma2;
-    h->calibrated[ci] = true;
+    if ((rc = check_fast_err(h))) return rc;
+    if ((rc = calibrate_fast(h, xdev, M, ci, &lc))) return rc;
   }
 
-  // ---- phase II / III: band selection, exact re-score; widen and repeat if the band shows larger errors --
-  const int LIST0_CAP = 1 << 16;   // scan survivors (~ subsample stride x q when the criterion is not flat)
-  const int THR_STRIDE = 32;
+  // ---- phase II / III: band selection + exact re-score, one stream-ordered pipeline per pass --------------------
+  const int BD = bd::BAND_DEV_MAX;
+  const int nslices = ld / bd::KSS_COLS + (ld % bd::KSS_COLS ? 1 : 0);
+  const int rd_grid = h->num_sms * 2, rd_warps = rd_grid * bd::RD_WARPS;
   CU_TRY(h->thr_key.reserve(2 * (size_t)q));
   CU_TRY(h->band_list0.reserve(LIST0_CAP));
   CU_TRY(h->band_list.reserve(LIST0_CAP));
   CU_TRY(h->band_count.reserve(2));
   CU_TRY(h->band_hiB.reserve((size_t)LIST0_CAP * q));
   CU_TRY(h->Xband.reserve((size_t)Mc * D));
+  CU_TRY(h->bd_kst.reserve((size_t)BD * ld));
+  CU_TRY(h->bd_ypart.reserve((size_t)nslices * BD));
+  CU_TRY(h->bd_part.reserve((size_t)rd_warps * BD * 2));
+  CU_TRY(h->bd_ctl.reserve(1));
+  if (!h->pin) CU_TRY(cudaHostAlloc(&h->pin, PIN_BYTES, cudaHostAllocDefault));
+  // pinned staging: [params q][BandCtl][best_val q][best_idx q]
+  double* pin_params = (double*)h->pin;
+  bd::BandCtl* pin_ctl = (bd::BandCtl*)(h->pin + (size_t)fk::BAND_MAX_Q * 8);
+  double* pin_bv = (double*)(pin_ctl + 1);
+  long long* pin_bi = (long long*)(pin_bv + fk::BAND_MAX_Q);
+  for (int c = 0; c < q; ++c) pin_params[c] = params ? params[c] : 0.0;
+  CU_TRY(cudaMemcpyAsync(h->params.p, pin_params, (size_t)q * 8, cudaMemcpyHostToDevice, st));
+  const size_t kss_smem = ((size_t)bd::KSS_ROWS * D + D + 1) * sizeof(double);
+  if (kss_smem > 48 * 1024)
+    CU_TRY(cudaFuncSetAttribute(bd::kstar_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kss_smem));
+
   int rescored = 0, passes = 0;
-  double dy = h->dy_cal[ci], ds = h->ds_cal[ci];
-  std::vector<long long> list;
+  double widen = h->widen[ci];
   for (;;) {
     ++passes;
-    std::vector<long long> ninf(2 * (size_t)q, fk::ord_key(-INFINITY));
-    CU_TRY(cudaMemcpyAsync(h->thr_key.p, ninf.data(), ninf.size() * 8, cudaMemcpyHostToDevice, st));
-    CU_TRY(cudaMemsetAsync(h->band_count.p, 0, 2 * sizeof(int), st));
-    CU_TRY(cudaStreamSynchronize(st));  // ninf is stack-owned
     fk::BandArgs b;
     b.yhat = h->f_yhat.p; b.sumsq = h->f_sumsq.p; b.dotf = h->f_dotf.p; b.params = h->params.p;
     b.M = M; b.acq = acq_id; b.minimize = minimize; b.estimate_trend = h->estimate_trend; b.q = q;
-    b.sigma2 = h->sigma2; b.plugin = plugin; b.G = h->G; b.dy = dy; b.ds = ds;
+    b.sigma2 = h->sigma2; b.plugin = plugin; b.G = h->G;
+    // half-widths: the larger of the a-priori model and the observed (calibrated) errors, times the widening factor
+    b.dy = widen * std::max(h->dy_cal[ci], h->use_model ? h->model.dy : 0.0);
+    b.ds = widen * h->ds_cal[ci];
+    b.ds_abs = h->use_model ? widen * h->model.ds_abs[ci] : 0.0;
+    b.ds_rel = h->use_model ? widen * h->model.ds_rel[ci] : 0.0;
+    b.du = h->use_model ? widen * h->model.du : 0.0;
+    h->last_band = b;
+    bd::band_reset_kernel<<<(std::max(2 * q, 2) + 255) / 256, 256, 0, st>>>(h->thr_key.p, 2 * q, fk::ord_key(-INFINITY), h->band_count.p,
+                                                                          h->best_val.p, h->best_idx.p, q, h->bd_ctl.p);
+    CU_TRY(cudaGetLastError());
     const long long ns = (M + THR_STRIDE - 1) / THR_STRIDE;
     fk::band_thr0_kernel<<<(int)std::min<long long>(h->num_sms * 4, (ns + 255) / 256), 256, 0, st>>>(b, THR_STRIDE, h->thr_key.p);
     CU_TRY(cudaGetLastError());
@@ -1654,58 +1835,103 @@ static int run_candidates_fast(b200bo_handle h, const double* Xc, int64_t M, int
     fk::band_filter_kernel<<<h->num_sms, 256, 0, st>>>(h->band_list0.p, h->band_count.p, LIST0_CAP, h->band_hiB.p,
                                                        h->thr_key.p + q, q, h->band_list.p, h->band_count.p + 1);
     CU_TRY(cudaGetLastError());
-    lc.all += 4;
-    int counts[2] = {0, 0};
-    CU_TRY(cudaMemcpyAsync(counts, h->band_count.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
-    CU_TRY(cudaStreamSynchronize(st));
-    const int count = counts[1];
-    if (nprod == 1 && (counts[0] > LIST0_CAP || count > RESCORE_DIRECT_MAX || passes > 2)) {
+    // exact float64 re-score of up to BAND_DEV_MAX band members, sizes read on the device
+    bd::band_gather_dev_kernel<<<(BD * D + 255) / 256, 256, 0, st>>>(xdev, h->band_list.p, h->band_count.p + 1, BD, D, h->Xband.p);
+    CU_TRY(cudaGetLastError());
+    bd::KstarSmallArgs ks;
+    ks.Xb = h->Xband.p; ks.Xt = h->Xt.p; ks.theta = h->theta.p; ks.gamma = h->gamma.p; ks.Kst = h->bd_kst.p;
+    ks.ypart = h->bd_ypart.p; ks.count = h->band_count.p + 1; ks.cap = BD; ks.N = h->N; ks.D = D; ks.ld = ld; ks.corr = h->corr;
+    bd::kstar_small_kernel<<<dim3(nslices, BD / bd::KSS_ROWS), bd::KSS_COLS, kss_smem, st>>>(ks);
+    CU_TRY(cudaGetLastError());
+    bd::RowdotArgs rd;
+    rd.Kst = h->bd_kst.p; rd.Linv = h->W.p; rd.Ft = h->Ft.p; rd.part = h->bd_part.p; rd.count = h->band_count.p + 1;
+    rd.cap = BD; rd.ld = ld;
+    bd::rowdot_kernel<<<rd_grid, 32 * bd::RD_WARPS, 0, st>>>(rd);
+    CU_TRY(cudaGetLastError());
+    bd::band_moments_kernel<<<BD, 128, 0, st>>>(h->bd_ypart.p, nslices, h->bd_part.p, rd_warps, h->band_count.p + 1, BD, h->beta,
+                                                h->yhat.p, h->sumsq.p, h->dotf.p);
+    CU_TRY(cudaGetLastError());
+    {
+      AcqArgs g{};
+      g.yhat = h->yhat.p; g.sumsq = h->sumsq.p; g.dotf = h->dotf.p;
+      g.M = BD; g.M_dev = h->band_count.p + 1; g.estimate_trend = h->estimate_trend; g.sigma2 = h->sigma2; g.G = h->G;
+      g.idx_map = h->band_list.p;
+      g.params = h->params.p; g.part_val = h->part_val.p; g.part_idx = h->part_idx.p;
+      g.acq = acq_id; g.minimize = minimize; g.q = q; g.plugin = plugin;
+      acq_kernel<<<dim3(1, q), 256, 0, st>>>(g);
+      CU_TRY(cudaGetLastError());
+      argmax_merge_kernel<<<(q + 63) / 64, 64, 0, st>>>(h->part_val.p, h->part_idx.p, 1, q, h->best_val.p, h->best_idx.p);
+      CU_TRY(cudaGetLastError());
+    }
+    bd::BandCheckArgs ck;
+    ck.y_fast = h->f_yhat.p; ck.ss_fast = h->f_sumsq.p; ck.df_fast = h->f_dotf.p;
+    ck.y_ex = h->yhat.p; ck.ss_ex = h->sumsq.p; ck.df_ex = h->dotf.p; ck.list = h->band_list.p;
+    ck.counts = h->band_count.p; ck.fused_err = h->err_flag.p; ck.cap = BD; ck.estimate_trend = h->estimate_trend;
+    ck.G = h->G; ck.sigma2 = h->sigma2; ck.dy = b.dy; ck.ds = b.ds; ck.ds_abs = b.ds_abs; ck.ds_rel = b.ds_rel; ck.du = b.du;
+    ck.ctl = h->bd_ctl.p;
+    bd::band_check_kernel<<<1, 256, 0, st>>>(ck);
+    CU_TRY(cudaGetLastError());
+    lc.all += 12;
+    CU_TRY(cudaMemcpyAsync(pin_ctl, h->bd_ctl.p, sizeof(bd::BandCtl), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(pin_bv, h->best_val.p, (size_t)q * 8, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(pin_bi, h->best_idx.p, (size_t)q * 8, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaEventRecord(e1, st));
+    CU_TRY(cudaStreamSynchronize(st));   // the one host round trip of the pass
+    if (pin_ctl->fused_err)
+      return set_err(B200BO_E_CUDA, "tensor-core pipeline wait timed out (code " + std::to_string(pin_ctl->fused_err) + ")");
+    const int count0 = pin_ctl->count0, count = pin_ctl->count;
+    if (nprod == 1 && (count0 > LIST0_CAP || count > RESCORE_DIRECT_MAX || passes > 2)) {
       // the one-product pass cannot separate the top of this criterion: three products for the rest of this fit
       h->escalate = true;
       return run_candidates_fast(h, Xc, M, loc, eval_mse, yhat_out, mse_out, acq_id, minimize, plugin, params, q,
                                  best_val, best_idx, fell_back);
     }
-    if (counts[0] > LIST0_CAP || passes > 4) {  // degenerate (flat criterion) or unstable error estimate
+    if (count0 > LIST0_CAP || passes > 4) {  // degenerate (flat criterion) or unstable error estimate
       *fell_back = true;
       return 0;
     }
-    list.resize(count);
-    CU_TRY(cudaMemcpyAsync(list.data(), h->band_list.p, (size_t)count * 8, cudaMemcpyDeviceToHost, st));
-    CU_TRY(cudaStreamSynchronize(st));
-    // exact fp64 moments + criteria of the band, Mc rows at a time; arg-max merged with the global indices
-    if ((rc = upload_params_reset_best(h, params, q))) return rc;
-    double ey_max = 0, es_max = 0;
-    for (int o = 0; o < count; o += Mc) {
-      const int m = std::min(Mc, count - o);
-      if (dev) {
-        fk::band_gather_kernel<<<(m * D + 255) / 256, 256, 0, st>>>(Xc, h->band_list.p + o, m, 0, D, h->Xband.p);
+    double ratio = pin_ctl->ratio;
+    h->last_err_y = pin_ctl->err_y; h->last_err_s = pin_ctl->err_s;
+    if (count > BD) {
+      // wide band: re-score it Mc rows at a time with the tile kernels of the float64 path (host-driven)
+      if ((rc = upload_params_reset_best(h, params, q))) return rc;
+      ratio = 0.0;
+      for (int o = 0; o < count; o += Mc) {
+        const int m = std::min(Mc, count - o);
+        fk::band_gather_kernel<<<(m * D + 255) / 256, 256, 0, st>>>(xdev, h->band_list.p + o, m, 0, D, h->Xband.p);
         CU_TRY(cudaGetLastError());
         ++lc.all;
-      } else if ((rc = host_rows_to(h->Xband.p, list.data() + o, m))) {
-        return rc;
+        if ((rc = fp64_moments(h, h->Xband.p, m, h->yhat.p, 1, nullptr, &lc))) return rc;
+        if ((rc = acq_stage(h, h->yhat.p, m, 0, h->band_list.p + o, acq_id, minimize, plugin, q, nullptr, 0, 0, nullptr, &lc)))
+          return rc;
+        bd::BandCheckArgs c2 = ck;
+        c2.list = h->band_list.p + o; c2.cap = m; c2.counts = h->band_count.p;  // counts[1] >= m here
+        CU_TRY(cudaMemsetAsync(h->bd_ctl.p, 0, sizeof(bd::BandCtl), st));
+        bd::band_check_kernel<<<1, 256, 0, st>>>(c2);
+        CU_TRY(cudaGetLastError());
+        CU_TRY(cudaMemcpyAsync(pin_ctl, h->bd_ctl.p, sizeof(bd::BandCtl), cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaStreamSynchronize(st));
+        ratio = std::max(ratio, pin_ctl->ratio);
+        h->last_err_y = std::max(h->last_err_y, pin_ctl->err_y);
+        h->last_err_s = std::max(h->last_err_s, pin_ctl->err_s);
       }
-      if ((rc = fp64_moments(h, h->Xband.p, m, h->yhat.p, 1, nullptr, &lc))) return rc;
-      if ((rc = acq_stage(h, h->yhat.p, m, 0, h->band_list.p + o, acq_id, minimize, plugin, q, nullptr, 0, 0, nullptr, &lc)))
-        return rc;
-      double ey, es;
-      if ((rc = fast_errors(h, h->band_list.p + o, 0, m, &ey, &es))) return rc;
-      ey_max = std::max(ey_max, ey);
-      es_max = std::max(es_max, es);
+      CU_TRY(cudaEventRecord(e1, st));
+      if ((rc = download_best(h, q, pin_bv, (int64_t*)pin_bi))) return rc;
     }
     rescored += count;
-    if (ey_max <= 0.5 * dy && es_max <= 0.5 * ds) break;  // the band was wide enough for the errors it shows
-    dy = std::max(dy, 4.0 * ey_max);
-    ds = std::max(ds, 4.0 * es_max);
-    h->dy_cal[ci] = std::max(h->dy_cal[ci], dy);
-    h->ds_cal[ci] = std::max(h->ds_cal[ci], ds);
+    h->last_ratio = ratio;
+    if (ratio <= 0.5) break;  // every error seen inside the band is within half of what the band allowed for
+    widen *= 4.0;             // larger errors than allowed for: widen and select again (no tensor-core work is redone)
+    h->widen[ci] = widen;
   }
   pt.end(2);
-  CU_TRY(cudaEventRecord(e1, st));
-  if ((rc = download_best(h, q, best_val, best_idx))) return rc;
-  CU_TRY(cudaStreamSynchronize(st));
+  for (int c = 0; c < q; ++c) {
+    best_val[c] = pin_bv[c];
+    best_idx[c] = pin_bi[c];
+  }
   float ms = 0;
   cudaEventElapsedTime(&ms, e0, e1);
-  h->timings[0] = ms; h->timings[1] = 0; h->timings[2] = pt.total(1); h->timings[3] = pt.total(2);
+  h->timings[0] = ms; h->timings[1] = 0; h->timings[2] = pt.total(1); h->timings[3] = ms - pt.total(1);
   h->timings[4] = fused_launches; h->timings[5] = lc.all; h->timings[6] = rescored; h->timings[7] = passes;
   h->timings[8] = nprod; h->timings[9] = (nprod == 3 && h->escalate) ? 1 : 0;
   return 0;
@@ -1968,6 +2194,73 @@ int b200bo_debug_fused_time(b200bo_handle h, const double* Xc_host, int64_t M, i
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   *out_ms = (double)ms / reps;
+  return 0;
+}
+
+int b200bo_get_band_info(b200bo_handle h, double* out, int n) {
+  CHECK_ARG(h && out && n >= 1, "bad argument");
+  if (!h->fast_ready) return set_err(B200BO_E_STATE, "no tensor-core state yet (run a B200BO_PREC_FAST call first)");
+  const FastModel& m = h->model;
+  const fk::BandArgs& b = h->last_band;
+  const double v[B200BO_N_BAND_INFO] = {
+      m.dy, m.du, m.ds_abs[0], m.ds_rel[0], m.ds_abs[1], m.ds_rel[1], m.det_ds, m.a_max, m.s2, m.fro, m.l1_max, m.gamma_l2,
+      m.f_l2, m.b_max, m.sd_r, h->dy_cal[0], h->ds_cal[0], h->dy_cal[1], h->ds_cal[1], h->cal_err_y[0], h->cal_err_s[0],
+      h->cal_err_y[1], h->cal_err_s[1], b.dy, b.ds, b.ds_abs, b.ds_rel, b.du, h->last_err_y, h->last_err_s, h->last_ratio,
+      std::max(h->widen[0], h->widen[1])};
+  for (int i = 0; i < n && i < B200BO_N_BAND_INFO; ++i) out[i] = v[i];
+  return 0;
+}
+
+int b200bo_debug_fast_check(b200bo_handle h, int64_t stride, int64_t max_samples, double* out, int n) {
+  CHECK_ARG(h && out && n >= 8 && stride >= 1 && max_samples >= 1, "bad argument");
+  if (!h->factored || !h->fast_ready || !h->last_fast.xdev)
+    return set_err(B200BO_E_STATE, "debug_fast_check needs a preceding tensor-core call on this factorisation");
+  CU_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  const int64_t M = h->last_fast.M;
+  const int D = h->D, Mc = h->Mc;
+  const int ci = h->last_fast.nprod == 1 ? 0 : 1;
+  const int64_t total = std::min<int64_t>((M + stride - 1) / stride, max_samples);
+  int rc;
+  if ((rc = ensure_predict_ws(h, 1, false))) return rc;
+  CU_TRY(h->band_list.reserve(LIST0_CAP));
+  CU_TRY(h->band_count.reserve(2));
+  CU_TRY(h->Xband.reserve((size_t)Mc * D));
+  CU_TRY(h->bd_ctl.reserve(1));
+  LaunchCount lc;
+  double ey = 0, es = 0, ra = 0;
+  // half-widths to compare with: those of the last band pass, or (after predict()) the model's for this product count
+  bd::BandCheckArgs ck;
+  ck.y_fast = h->f_yhat.p; ck.ss_fast = h->f_sumsq.p; ck.df_fast = h->f_dotf.p;
+  ck.y_ex = h->yhat.p; ck.ss_ex = h->sumsq.p; ck.df_ex = h->dotf.p; ck.list = h->band_list.p;
+  ck.counts = h->band_count.p; ck.fused_err = h->err_flag.p; ck.estimate_trend = h->estimate_trend;
+  ck.G = h->G; ck.sigma2 = h->sigma2;
+  ck.dy = std::max(h->model.dy, h->calibrated[ci] ? h->dy_cal[ci] : 0.0) * h->widen[ci];
+  ck.ds = (h->calibrated[ci] ? h->ds_cal[ci] : 0.0) * h->widen[ci];
+  ck.ds_abs = h->model.ds_abs[ci] * h->widen[ci]; ck.ds_rel = h->model.ds_rel[ci] * h->widen[ci]; ck.du = h->model.du * h->widen[ci];
+  ck.ctl = h->bd_ctl.p;
+  const int step = std::min(Mc, LIST0_CAP);
+  for (int64_t o = 0; o < total; o += step) {
+    const int m = (int)std::min<int64_t>(step, total - o);
+    fk::iota_stride_kernel<<<(m + 255) / 256, 256, 0, st>>>(h->band_list.p, m, stride);
+    fk::list_offset_kernel<<<(m + 255) / 256, 256, 0, st>>>(h->band_list.p, m, o * stride);
+    fk::band_gather_kernel<<<(int)(((size_t)m * D + 255) / 256), 256, 0, st>>>(h->last_fast.xdev, h->band_list.p, m, 0, D, h->Xband.p);
+    CU_TRY(cudaGetLastError());
+    if ((rc = fp64_moments(h, h->Xband.p, m, h->yhat.p, 1, nullptr, &lc))) return rc;
+    const int cnt[2] = {m, m};
+    CU_TRY(cudaMemcpyAsync(h->band_count.p, cnt, sizeof cnt, cudaMemcpyHostToDevice, st));
+    ck.cap = m;
+    bd::band_check_kernel<<<1, 256, 0, st>>>(ck);
+    CU_TRY(cudaGetLastError());
+    bd::BandCtl c;
+    CU_TRY(cudaMemcpyAsync(&c, h->bd_ctl.p, sizeof c, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    ey = std::max(ey, c.err_y);
+    es = std::max(es, c.err_s);
+    ra = std::max(ra, c.ratio);
+  }
+  out[0] = (double)total; out[1] = ey; out[2] = es; out[3] = ra;
+  out[4] = ck.dy; out[5] = ck.ds; out[6] = ck.ds_abs + ck.ds_rel; out[7] = h->last_fast.nprod;
   return 0;
 }
 

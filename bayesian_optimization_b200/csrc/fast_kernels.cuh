@@ -545,7 +545,12 @@ struct BandArgs {
   long long M;
   int acq, minimize, estimate_trend, q;
   double sigma2, plugin, G;
-  double dy, ds;  // half-widths of the error intervals of yhat and mse
+  // half-widths of the error intervals.  yhat: dy.  mse of candidate i:
+  //   max(ds, ds_abs + ds_rel * sqrt(sum rt_i^2)) + sigma2 (2 |u_i| du + du^2)
+  // ds = the calibrated (observed) width, ds_abs / ds_rel = the a-priori rounding model of the tensor-core pass (its
+  // standard deviation grows with ||rt||), du = half-width of u = (Ft^T rt - 1) / G        (all in mse units but du)
+  double dy, ds;
+  double ds_abs = 0.0, ds_rel = 0.0, du = 0.0;
 };
 
 struct Box {
@@ -558,13 +563,15 @@ __device__ __forceinline__ Box band_box(const BandArgs& p, long long i) {
     const double u = (p.dotf[i] - 1.0) / p.G;
     u2 = u * u;
   }
-  const double mse = (1.0 - p.sumsq[i] + u2) * p.sigma2;  // unclipped; the interval ends are clipped (gpr.py:510)
+  const double ss = p.sumsq[i];
+  const double mse = (1.0 - ss + u2) * p.sigma2;  // unclipped; the interval ends are clipped (gpr.py:510)
   const double y = p.minimize ? p.yhat[i] : -p.yhat[i];
+  const double ds = fmax(p.ds, p.ds_abs + p.ds_rel * sqrt(fmax(ss, 0.0) + 1e-3)) + (2.0 * sqrt(u2) * p.du + p.du * p.du) * p.sigma2;
   Box b;
   b.ylo = y - p.dy;
   b.yhi = y + p.dy;
-  b.s0 = sqrt(fmax(mse - p.ds, 0.0));
-  b.s1 = sqrt(fmax(mse + p.ds, 0.0));
+  b.s0 = sqrt(fmax(mse - ds, 0.0));
+  b.s1 = sqrt(fmax(mse + ds, 0.0));
   return b;
 }
 
@@ -728,28 +735,20 @@ __global__ void __launch_bounds__(256) band_scan_kernel(BandArgs p, const long l
   }
 }
 
-// 3. exact bounds of the listed candidates: hiB (n, q) and thr1_key[c] = max lower bound
+// 3. exact bounds of the listed candidates: hiB (n, q) and thr1_key[c] = max lower bound.  One thread per (entry,
+//    criterion) pair -- the list holds tens of entries, a loop over the criteria would leave the GPU idle.
 __global__ void __launch_bounds__(256) band_refine_kernel(BandArgs p, const long long* __restrict__ list,
                                                           const int* __restrict__ count, int cap,
                                                           double* __restrict__ hiB, long long* __restrict__ thr_key) {
-  __shared__ double par_s[BAND_MAX_Q];
-  for (int c = threadIdx.x; c < p.q; c += blockDim.x) par_s[c] = band_par(p, c);
-  __syncthreads();
   const int n = min(*count, cap);
-  for (int b0 = blockIdx.x * blockDim.x; b0 < n; b0 += gridDim.x * blockDim.x) {
-    const int bi = b0 + threadIdx.x;
-    const bool on = bi < n;
-    Box b;
-    if (on) b = band_box(p, list[bi]);
-    for (int c = 0; c < p.q; ++c) {
-      double lo = -INFINITY;
-      if (on) {
-        lo = band_lo(p, b, par_s[c]);
-        hiB[(size_t)bi * p.q + c] = band_hi(p, b, par_s[c]);
-      }
-      for (int o = 16; o; o >>= 1) lo = fmax(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-      if ((threadIdx.x & 31) == 0 && lo > -INFINITY) atomicMax(thr_key + c, ord_key(lo));
-    }
+  const long long total = (long long)n * p.q;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int bi = (int)(e / p.q), c = (int)(e % p.q);
+    const Box b = band_box(p, list[bi]);
+    const double par = band_par(p, c);
+    hiB[e] = band_hi(p, b, par);
+    const double lo = band_lo(p, b, par);
+    if (lo > -INFINITY) atomicMax(thr_key + c, ord_key(lo));
   }
 }
 
@@ -764,6 +763,17 @@ __global__ void __launch_bounds__(256) band_filter_kernel(const long long* __res
     for (int c = 0; c < q && !in; ++c) in = hiB[(size_t)bi * q + c] >= ord_val(thr_key[c]);
     if (in) out[atomicAdd(out_count, 1)] = list[bi];
   }
+}
+
+// list[i] = i * stride (the strided calibration / check samples)
+__global__ void iota_stride_kernel(long long* __restrict__ list, int n, long long stride) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) list[i] = (long long)i * stride;
+}
+
+__global__ void list_offset_kernel(long long* __restrict__ list, int n, long long off) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) list[i] += off;
 }
 
 // Xb[b, :] = Xc[list[b] - idx_base, :]

@@ -261,6 +261,7 @@ struct AcqArgs {
   long long* part_idx;   // (q, gridDim.x)
   long long idx_base;    // global index of candidate 0 of this chunk
   const long long* idx_map;  // NULL, or global index of candidate i (re-scored band of the fast path)
+  const int* M_dev = nullptr;  // NULL, or the candidate count in device memory (then M is its cap)
   int M, acq, minimize, estimate_trend, q;
   double sigma2, plugin, G;  // G: the 1x1 triangular factor of the thin QR of Ft (|G| = ||Ft||)
 };
@@ -283,7 +284,8 @@ __global__ void __launch_bounds__(256) acq_kernel(AcqArgs p) {
   const double par = p.acq == ACQ_MGFI ? fmin(p.params[c], 22.36) : p.params[c];  // acquisition_fun.py:262
   double bv = 0.0;
   long long bi = -1;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.M; i += gridDim.x * blockDim.x) {
+  const int M = p.M_dev ? min(*p.M_dev, p.M) : p.M;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < M; i += gridDim.x * blockDim.x) {
     double mse = mse_from_sums(p, i);
     if (c == 0 && p.mse_out) p.mse_out[i] = mse;
     double v = acq_value(p.acq, p.yhat[i], mse, p.sigma2, p.plugin, par, p.minimize);

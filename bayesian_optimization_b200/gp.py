@@ -174,6 +174,9 @@ class GaussianProcess:
         self.X, self.y = np.ascontiguousarray(X, dtype=np.float64), np.ascontiguousarray(y, dtype=np.float64)
         self._check_params()
         self._cache = {}
+        if self.estimate_trend and self._p > self.X.shape[0]:  # gpr.py:298-309: beta cannot be estimated from fewer rows
+            raise Exception("Ordinary least squares problem is undetermined n_samples=%d must be greater than the "
+                            "regression model size p=%d." % (self.X.shape[0], self._p))
         self.engine.set_train(self.X, self.y[:, 0])
         if self.estimate_trend:
             self.F = self.mean.F(self.X)

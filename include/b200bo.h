@@ -196,6 +196,31 @@ int b200bo_acq_grad(b200bo_handle h, const double* Xc, int64_t M, int acq_id, in
  * fused tensor-core kernel alone over M host candidates (no band stage, results discarded); products = 1 or 3. */
 int b200bo_debug_fused_time(b200bo_handle h, const double* Xc_host, int64_t M, int products, int reps, double* out_ms);
 
+/* -- exactness of the arg-max on the tensor-core path: what the band stage allowed for, what it observed --------------
+ * The band of b200bo_acq (B200BO_PREC_FAST) holds every candidate whose criterion could still be the maximum once the
+ * fast pass's error is allowed for; it is re-scored in float64.  Half-widths: yhat +- dy; mse of candidate i +-
+ * max(ds_cal, ds_abs + ds_rel sqrt(sum rt_i^2)) + sigma2 (2 |u_i| du + du^2), where (dy, du, ds_abs, ds_rel) come from
+ * an A-PRIORI rounding model built at factor() time from ||L^-1|| (row norms, spectral and Frobenius norm), ||gamma||,
+ * ||L^-T Ft|| and the kernel's slope (8 modelled standard deviations) and (dy_cal, ds_cal) = 8 x the
+ * largest fast-vs-float64 error on a strided 2048-candidate sample of the first call after factor().  Every pass also
+ * compares the errors it sees inside the band with what it allowed for and widens x4 + repeats above one half.
+ *   out[0] dy model  [1] du model  [2] ds_abs, [3] ds_rel (one product)  [4] ds_abs, [5] ds_rel (three products)
+ *   [6] deterministic worst-case bound on the mse error (for the record: it is never the binding one)
+ *   [7] max row 2-norm of L^-1  [8] ||L^-1||_2 (power iteration + 25 %)  [9] ||L^-1||_F  [10] max row 1-norm
+ *   [11] ||gamma||_2  [12] ||L^-T Ft||_2  [13] max ||x_j||^2 in kernel units  [14] modelled sd of one fp32 r entry
+ *   [15] dy_cal, [16] ds_cal (one product)  [17] dy_cal, [18] ds_cal (three)  [19..22] largest calibration errors
+ *   (y, mse) x (one, three products)  [23..27] dy, ds, ds_abs, ds_rel, du of the LAST band pass
+ *   [28] max |yhat error|, [29] max |mse error| seen inside the last band  [30] their largest ratio to the allowance
+ *   [31] widening factor in force */
+#define B200BO_N_BAND_INFO 32
+int b200bo_get_band_info(b200bo_handle h, double* out, int n);
+/* test / bench hook: float64 moments of every stride-th candidate (at most max_samples) of the LAST tensor-core call
+ * (b200bo_acq or b200bo_predict with B200BO_PREC_FAST; device-resident input must still be alive) against the moments
+ * that call produced:  out[0] candidates checked  [1] max |yhat_fast - yhat|  [2] max |mse_fast - mse| (unclipped)
+ * [3] largest (error / allowed half-width)  [4] dy  [5] ds_cal  [6] ds_abs + ds_rel in force  [7] products per MAC.
+ * What it checks against: gpr.py:486-505 evaluated in float64 on the device (itself pinned to the reference goldens). */
+int b200bo_debug_fast_check(b200bo_handle h, int64_t stride, int64_t max_samples, double* out, int n);
+
 /* -- environment knobs read at b200bo_create (developer / A-B switches; the defaults are the measured best) --------
  *   B200BO_FAST_KERNEL=1..5      generation of the fused tensor-core kernel (default 5), = b200bo_set_fast_kernel
  *   B200BO_FAST_PRODUCTS=1|3     fp16 products per MAC of the first acquisition pass (default 1)
@@ -203,6 +228,8 @@ int b200bo_debug_fused_time(b200bo_handle h, const double* Xc_host, int64_t M, i
  *   B200BO_CHOL_LOOKAHEAD=0|1|2  Cholesky: single stream | look-ahead, separate kernels | fused panel step where faster
  *   B200BO_GRAPHS=0|1            CUDA-graph replay of the factorisation stretches for N <= 2048 (default 1)
  *   B200BO_WAIT_HINT_NS=n        suspend-time hint of the mbarrier waits in the fused kernels
+ *   B200BO_BAND_MODEL=0|1        0: band half-widths from the calibration sample only (round-1 behaviour)
+ *   B200BO_DEV_CHUNK_TILES=n     device-resident input: fused launches of n candidate tiles per SM (0 = one launch)
  *   B200BO_TRACE=path            dump a clock64 timeline of CTA 0 of the fused kernel (Matern-5/2, one product) */
 
 /* -- instrumentation ------------------------------------------------------------------------------------
