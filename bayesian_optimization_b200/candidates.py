@@ -50,14 +50,44 @@ def _bounds_of(search_space) -> np.ndarray:
     return b
 
 
-def sample_candidates(search_space, M: int, rng: Optional[np.random.Generator] = None) -> np.ndarray:
-    """(M, D) float64 uniform candidates: ``search_space.sample(N, method="uniform")`` when the space provides it
-    (search_space.py:742-754) and no generator is forced, else numpy on the bounds."""
+SAMPLING_METHODS = ("uniform", "LHS", "sobol")
+
+
+def sample_candidates(search_space, M: int, rng: Optional[np.random.Generator] = None, method: str = "uniform") -> np.ndarray:
+    """(M, D) float64 candidates by one of the designs of ``SearchSpace._sample`` (search_space.py:742-754):
+    "uniform", "LHS" (Latin hypercube) or "sobol".  When the space has a ``sample`` method and no generator is
+    forced, that method is called (``search_space.sample(N, method=...)``: upstream's own code, pyDOE / sobol_seq
+    included); on plain bounds the designs are built here:
+      * LHS: one point per stratum and coordinate, strata permuted independently per coordinate.  (Upstream asks
+        pyDOE for its "maximin" variant -- the best of five such designs by smallest pairwise distance, an O(M^2)
+        criterion that is out of reach for 1e6 candidates; the stratification is what matters for a scoring pass.)
+      * sobol: the unscrambled Sobol sequence after the origin, as ``i4_sobol_generate(dim, N)`` (skip = 1) returns it,
+        from scipy's generator (Joe-Kuo direction numbers, up to 21201 dimensions)."""
+    if method not in SAMPLING_METHODS:
+        raise ValueError("method should be one of %s, %s was given." % (list(SAMPLING_METHODS), method))
+    M = int(M)
     if rng is None and hasattr(search_space, "sample"):
-        return np.ascontiguousarray(np.asarray(search_space.sample(N=int(M), method="uniform"), dtype=np.float64))
+        return np.ascontiguousarray(np.asarray(search_space.sample(N=M, method=method), dtype=np.float64))
     b = _bounds_of(search_space)
+    D = b.shape[0]
     rng = np.random.default_rng() if rng is None else rng
-    return b[:, 0] + (b[:, 1] - b[:, 0]) * rng.random((int(M), b.shape[0]))
+    if method == "uniform" or (method == "LHS" and M == 1):  # search_space.py:748-749: one LHS point is a uniform draw
+        U = rng.random((M, D))
+    elif method == "LHS":
+        U = np.empty((M, D))
+        for d in range(D):
+            U[:, d] = (rng.permutation(M) + rng.random(M)) / M
+    else:
+        from scipy.stats import qmc
+
+        s = qmc.Sobol(d=D, scramble=False)
+        s.fast_forward(1)
+        import warnings
+
+        with warnings.catch_warnings():  # scipy warns when M is not a power of two; any prefix of the sequence is wanted here
+            warnings.simplefilter("ignore")
+            U = s.random(M)
+    return b[:, 0] + (b[:, 1] - b[:, 0]) * U
 
 
 def _is_duplicate(x: np.ndarray, data: Optional[np.ndarray]) -> bool:
@@ -129,15 +159,17 @@ def argmax_candidates(
     data: Optional[np.ndarray] = None,
     rng: Optional[np.random.Generator] = None,
     max_constraint_checks: int = 32768,
+    sampling: str = "uniform",
 ):
     """Drop-in for ``argmax_restart``.  ``eval_budget`` x ``n_restart`` (the reference's total number of single-point
     evaluations) scales the default candidate count: max(2^16, 1024 x eval_budget x n_restart), capped at 2^22.
     ``data``: evaluated points (N, D) to de-duplicate against; ``wait_iter`` is accepted for signature
-    compatibility (there are no sequential restarts to stop early)."""
+    compatibility (there are no sequential restarts to stop early); ``sampling``: "uniform" | "LHS" | "sobol", the
+    designs of ``SearchSpace._sample`` (search_space.py:742-754)."""
     crit = unwrap_criterion(obj_func)
     bounds = _bounds_of(search_space)
     M = int(n_candidates) if n_candidates else int(min(2**22, max(2**16, 1024 * int(eval_budget) * int(n_restart))))
-    Xc = sample_candidates(search_space, M, rng)
+    Xc = sample_candidates(search_space, M, rng, sampling)
     if Xc.ndim != 2 or Xc.shape[1] != bounds.shape[0]:
         raise ValueError("sampled candidates do not match the bounds")
     vals, exact = rank_values(crit, Xc)

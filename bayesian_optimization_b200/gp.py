@@ -108,6 +108,8 @@ class GaussianProcess:
         self.precision = precision
         self._engine: Optional[Engine] = None
         self._cache = {}
+        self._pool = []      # extra engine handles of the concurrent hyper-parameter restarts: [engine, training-set generation]
+        self._train_gen = 0
         self._sub = None  # multi-target y (N, k > 1): one single-target model per column (same R, own Yt / rho / gamma)
 
     # ---- engine plumbing ---------------------------------------------------------------------------
@@ -124,12 +126,35 @@ class GaussianProcess:
                     self._refactor()
         return self._engine
 
+    def _engine_pool(self, n: int):
+        """``n`` engine handles that hold this model's training set, the primary one first.  The extra handles (own
+        CUDA stream, own factorisation buffers) let the restarts of the hyper-parameter search run concurrently; they
+        are kept for the next fit() of a BO loop and follow the training set lazily."""
+        if self._sub or n <= 1:
+            return [self.engine]
+        pool = [e for e in getattr(self, "_pool", [])][: n - 1]
+        while len(pool) < n - 1:
+            pool.append([Engine(self.device), -1])
+        for slot in pool:
+            if slot[1] != self._train_gen:
+                slot[0].set_train(self.X, self.y[:, 0])
+                slot[1] = self._train_gen
+        self._pool = pool
+        return [self.engine] + [slot[0] for slot in pool]
+
+    def close_pool(self):
+        """release the extra engine handles of the hyper-parameter search (3 N^2 float64 matrices each)"""
+        for slot in getattr(self, "_pool", []):
+            slot[0].close()
+        self._pool = []
+
     def __getstate__(self):
         # dill/pickle (BaseBO.save, base.py:499-519; joblib workers, bayes_opt.py:108-111): drop the device
-        # handle and the lazily fetched arrays; the deterministic factorisation is redone on first use.
+        # handles and the lazily fetched arrays; the deterministic factorisation is redone on first use.
         st = self.__dict__.copy()
         st["_engine"] = None
         st["_cache"] = {}
+        st["_pool"] = []
         return st
 
     def __setstate__(self, st):
@@ -174,6 +199,7 @@ class GaussianProcess:
         self.X, self.y = np.ascontiguousarray(X, dtype=np.float64), np.ascontiguousarray(y, dtype=np.float64)
         self._check_params()
         self._cache = {}
+        self._train_gen = getattr(self, "_train_gen", 0) + 1
         if self.estimate_trend and self._p > self.X.shape[0]:  # gpr.py:298-309: beta cannot be estimated from fewer rows
             raise Exception("Ordinary least squares problem is undetermined n_samples=%d must be greater than the "
                             "regression model size p=%d." % (self.X.shape[0], self._p))
@@ -242,29 +268,45 @@ class GaussianProcess:
     def _beta_fixed(self):
         return None if self.estimate_trend else np.asarray(self.mean.beta, dtype=np.float64).ravel()
 
-    def _factor(self, par):
+    def _factor(self, par, engine=None):
         theta, last = self._split_par(par)
         nv = float(np.atleast_1d(self.noise_var)[0]) if self.estimation_mode == "noisy" else 0.0
-        llf, s2, nvo, status = self.engine.factor(self._corr_id, self._theta_dev(theta), _MODES[self.estimation_mode], last, nv,
-                                                  self._trend_id, self._beta_fixed())
+        llf, s2, nvo, status = (engine or self.engine).factor(self._corr_id, self._theta_dev(theta), _MODES[self.estimation_mode],
+                                                              last, nv, self._trend_id, self._beta_fixed())
         self._cache = {}
         return llf, s2, nvo, status
+
+    def _likelihood_on(self, engine, par, restricted=False, env=None, eval_grad=False):
+        """the likelihood (and gradient) at ``par`` evaluated on a given engine handle -- what one restart of the
+        hyper-parameter search calls; the public methods below run it on the model's primary handle"""
+        n_par = np.size(par)
+        fail = (-np.inf, np.zeros((n_par, 1))) if eval_grad else -np.inf
+        if restricted:
+            if self._sub:
+                raise NotImplementedError("the restricted likelihood is implemented for one target")
+            theta, s2, nv = self._split_par_restricted(par)
+            llf, status = engine.factor_restricted(self._corr_id, self._theta_dev(theta), s2, nv, self._trend_id, self._beta_fixed())
+            self._cache = {}
+            if status != _lib.FIT_OK:
+                return fail
+            if env is not None:
+                env["sigma2"] = s2
+                env["noise_var"] = nv
+            return (llf, engine.llf_grad_restricted(n_par).reshape(-1, 1)) if eval_grad else llf
+        if self._sub:
+            return self._llf_multi(par, env, eval_grad)
+        llf, s2, nvo, status = self._factor(par, engine)
+        if status != _lib.FIT_OK:
+            return fail
+        if env is not None:
+            env["sigma2"] = np.atleast_1d(s2)
+            env["noise_var"] = nvo
+        return (llf, engine.llf_grad(n_par)) if eval_grad else llf
 
     def log_likelihood_concentrated(self, par, env=None, eval_grad=False):
         """Concentrated log-likelihood at ``par`` on the device; -inf when the factorisation fails or the
         value is positive (gpr.py:981-982).  ``env`` receives sigma2 / noise_var like the reference's."""
-        if self._sub:
-            return self._llf_multi(par, env, eval_grad)
-        llf, s2, nvo, status = self._factor(par)
-        n_par = np.size(par)
-        if status != _lib.FIT_OK:
-            return (-np.inf, np.zeros((n_par, 1))) if eval_grad else -np.inf
-        if env is not None:
-            env["sigma2"] = np.atleast_1d(s2)
-            env["noise_var"] = nvo
-        if eval_grad:
-            return llf, self.engine.llf_grad(n_par)
-        return llf
+        return self._likelihood_on(None if self._sub else self.engine, par, False, env, eval_grad)
 
     def _split_par_restricted(self, par):
         """gpr.py:826-835: (theta, sigma2, noise_var) per estimation mode"""
@@ -278,20 +320,7 @@ class GaussianProcess:
     def log_likelihood_restricted(self, par, env=None, eval_grad=False):
         """Restricted (REML) log-likelihood at ``par`` on the device (gpr.py:813-918); -inf when the factorisation
         fails (:842-847) or exp(llf) > 1 (:872-875).  ``env`` receives sigma2 / noise_var as upstream (:904-906)."""
-        if self._sub:
-            raise NotImplementedError("the restricted likelihood is implemented for one target")
-        theta, s2, nv = self._split_par_restricted(par)
-        n_par = np.size(par)
-        llf, status = self.engine.factor_restricted(self._corr_id, self._theta_dev(theta), s2, nv, self._trend_id, self._beta_fixed())
-        self._cache = {}
-        if status != _lib.FIT_OK:
-            return (-np.inf, np.zeros((n_par, 1))) if eval_grad else -np.inf
-        if env is not None:
-            env["sigma2"] = s2
-            env["noise_var"] = nv
-        if eval_grad:
-            return llf, self.engine.llf_grad_restricted(n_par).reshape(-1, 1)
-        return llf
+        return self._likelihood_on(self.engine, par, True, env, eval_grad)
 
     def _refactor(self):
         if getattr(self, "_restricted_par", None) is not None:

@@ -131,3 +131,42 @@ def test_fast_precision_ranking_matches_float64_choice():
                                          rng=np.random.default_rng(4), refine_steps=0)
     assert res["fast"][0] == res["fp64"][0]
     assert res["fast"][1] == pytest.approx(res["fp64"][1], rel=1e-9)
+
+
+@pytest.mark.parametrize("method", ["uniform", "LHS", "sobol"])
+def test_sampling_designs(method):
+    """the three designs of SearchSpace._sample (search_space.py:742-754) on plain bounds"""
+    from bayesian_optimization_b200.candidates import sample_candidates
+
+    b = np.array([[-5.0, 5.0], [0.0, 1.0], [10.0, 30.0]])
+    M = 1024
+    X = sample_candidates(b, M, rng=np.random.default_rng(3), method=method)
+    assert X.shape == (M, 3) and X.dtype == np.float64
+    assert np.all(X >= b[:, 0]) and np.all(X <= b[:, 1])
+    U = (X - b[:, 0]) / (b[:, 1] - b[:, 0])
+    if method == "LHS":      # exactly one point per stratum and coordinate
+        for d in range(3):
+            assert np.array_equal(np.sort(np.floor(U[:, d] * M).astype(int)), np.arange(M))
+    if method == "sobol":    # a (t, m, s)-net with the origin skipped: points 1 .. M-1 fill every dyadic slab but the first
+        for d in range(3):
+            assert np.array_equal(np.sort(np.floor(U[: M - 1, d] * M).astype(int)), np.arange(1, M))
+        assert U[0].tolist() == [0.5, 0.5, 0.5]
+    assert sample_candidates(b, 1, rng=np.random.default_rng(0), method="LHS").shape == (1, 3)
+    with pytest.raises(ValueError):
+        sample_candidates(b, 4, method="halton")
+
+
+def test_sampling_goes_through_the_space_when_it_can():
+    """a search space with its own ``sample`` (upstream's SearchSpace) is asked, with the method passed on"""
+    from bayesian_optimization_b200.candidates import sample_candidates
+
+    class Space:
+        bounds = [[0.0, 1.0], [0.0, 2.0]]
+
+        def sample(self, N, method):
+            self.asked = (N, method)
+            return [[0.5, 1.0]] * N
+
+    sp = Space()
+    X = sample_candidates(sp, 5, method="sobol")
+    assert sp.asked == (5, "sobol") and X.shape == (5, 2)

@@ -194,3 +194,58 @@ def test_acquisition_classes_plumbing_vs_reference(name):
     x, v = b2.argmax_candidates(functools.partial(ei, return_dx=False), [[-1, 2]] * D, n_candidates=2000,
                                 rng=np.random.default_rng(0), refine_steps=0 if int(c["corr"]) == go.CORR_MATERN52 else 3)
     assert len(x) == D and v >= ei(np.array([x]))[0] * (1 - 1e-9)
+
+
+def _sequential_search(gp):
+    """the search as a plain sequential loop (what gpr.py:1127-1162 does), written for this test: one restart after the
+    other on the model's primary engine, each start point drawn when its turn comes"""
+    from scipy.optimize import fmin_l_bfgs_b
+
+    from bayesian_optimization_b200 import hyperopt as ho
+
+    box = ho.parameter_box(gp)
+    budget = 200 * box.n if gp.eval_budget is None else gp.eval_budget
+    obj = ho.NegLikelihood(gp, gp.engine, gp.likelihood == "restricted")
+    z0 = ho.first_start(gp, box)
+    best, waited, used = None, 0, 0
+    for i in range(gp.random_start):
+        if i:
+            z0 = np.random.uniform(box.lo, box.hi)
+        z, f, info = fmin_l_bfgs_b(obj, z0, bounds=box.bounds, maxfun=budget)
+        if best is None:
+            best = (z, f)
+        elif f <= best[1]:
+            best, waited = (z, f), 0
+        else:
+            waited += 1
+        used += info["funcalls"]
+        budget -= info["funcalls"]
+        if budget <= 0 or waited >= gp.wait_iter:
+            break
+    return 10.0 ** best[0], -best[1], used
+
+
+@pytest.mark.parametrize("random_start,eval_budget,wait_iter", [(1, None, 5), (3, None, 5), (7, None, 5), (7, 60, 5),
+                                                              (6, 25, 5), (7, None, 1), (5, 200, 2)])
+@pytest.mark.parametrize("name", ["rbf_ny", "m32_ny", "rbf_ne"])
+def test_concurrent_restarts_equal_the_sequential_loop(name, random_start, eval_budget, wait_iter):
+    """the waves of concurrent restarts (hyperopt.py) give the sequential loop's parameters, likelihood, evaluation count
+    AND leave numpy's global generator in the same state -- also when the budget binds inside a wave or the stagnation
+    counter stops it early"""
+    c = FITS[name]
+    D, mode, kw = _kwargs(c)
+    kw.update(random_start=random_start, eval_budget=eval_budget, wait_iter=wait_iter)
+    kw.pop("theta0")  # the first start is drawn too
+    a = b2.GaussianProcess(mean=b2.constant_trend(D), **kw)
+    b = b2.GaussianProcess(mean=b2.constant_trend(D), **kw)
+    np.random.seed(11)
+    a.fit(c["X"], c["y"])
+    state_a = np.random.get_state()
+    np.random.seed(11)
+    b._check_data(c["X"], c["y"])
+    par, llf, used = _sequential_search(b)
+    state_b = np.random.get_state()
+    assert a.eval_count == used
+    assert a.log_likelihood_ == pytest.approx(llf, rel=1e-12)
+    np.testing.assert_allclose(np.r_[a.par["theta"], [a.par[k][0] for k in a.par if k != "theta"]], par, rtol=1e-12)
+    assert state_a[0] == state_b[0] and np.array_equal(state_a[1], state_b[1]) and state_a[2:] == state_b[2:]
