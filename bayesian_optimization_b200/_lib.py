@@ -73,6 +73,7 @@ SIGNATURES = {
                                           C.c_void_p]),
     "b200bo_debug_fast_rt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_void_p]),
+    "b200bo_best_pairs_device": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p]),
     "b200bo_get_band_info": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "b200bo_debug_fast_check": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int]),
     "b200bo_get_timings": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
@@ -268,6 +269,11 @@ class Engine:
                                     float(plugin), params.ctypes.data, q, _ptr(vals), best_val.ctypes.data,
                                     best_idx.ctypes.data))
         return best_val, best_idx, vals
+
+    def best_pairs_device(self, out, index_offset: int, rank: int, world: int):
+        """after acq(): this rank's (value bits, global index) pairs into row ``rank`` of the (world, 2q) int64 CUDA
+        tensor ``out`` (other rows zeroed), ordered on the handle's stream -- the payload of the one all-reduce"""
+        _check(self._lib.b200bo_best_pairs_device(self._h, int(index_offset), int(rank), int(world), C.c_void_p(_ptr(out))))
 
     def acq_from_moments(self, yhat, mse, acq_id: int, minimize: bool, plugin: float, params,
                          return_values: bool = True):

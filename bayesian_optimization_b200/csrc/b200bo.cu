@@ -52,6 +52,21 @@ static int set_err(int code, const std::string& msg) {
 
 namespace {
 
+// (world, 2 q) int64 exchange block of the global arg-max: this rank's row <- [value bits | global index], other rows
+// <- 0, so that ONE integer sum over the ranks (ncclAllReduce) delivers every rank's pairs bit for bit
+__global__ void best_pairs_kernel(const double* __restrict__ best_val, const long long* __restrict__ best_idx, int q,
+                                  long long offset, int rank, int world, long long* __restrict__ out) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= world * 2 * q) return;
+  const int r = e / (2 * q), c = e % (2 * q);
+  long long v = 0;
+  if (r == rank) {
+    if (c < q) v = __double_as_longlong(best_val[c]);
+    else v = best_idx[c - q] >= 0 ? best_idx[c - q] + offset : -1;
+  }
+  out[e] = v;
+}
+
 template <typename T>
 struct DevBuf {
   T* p = nullptr;
@@ -208,6 +223,7 @@ struct b200bo_ctx {
   double last_err_y = 0, last_err_s = 0, last_ratio = 0;
   fk::BandArgs last_band{};
   LastFast last_fast;
+  int last_q = 0;                 // criteria of the last acquisition call (b200bo_best_pairs_device)
   int dev_chunk_tiles = 0;        // B200BO_DEV_CHUNK_TILES: fused launches of this many tiles per SM on device-resident input
   std::vector<double> Xhost;      // training set as given (N, D): the distance-error bound needs max_j ||x_j||^2 per theta
   DevBuf<double> Xall, f_mse, bd_kst, bd_ypart, bd_part, pm_v, pm_t, pm_t2, rowsq, rowl1;
@@ -1612,9 +1628,11 @@ static void build_fast_model(b200bo_ctx* h, const std::vector<double>& rowsq, co
   m.a_max = sqrt(amax2); m.s2 = sqrt(s2_sq); m.fro = sqrt(fro2); m.l1_max = l1max;
   m.gamma_l2 = gamma_l2; m.f_l2 = f_l2; m.b_max = b_max;
   // per-element error of the fp32 cross-correlation: slope of the kernel in its argument x error of the fp32 squared
-  // distance (three split-fp16 Gram products + fp32 adds: ~2^-21 of a_m + b_j as one standard deviation; the product
-  // |phi'(acc)| (a_m + b_j) is bounded over all candidates by K_phi max(5 b_max, 8): far candidates have r ~ 0)
-  const double e_acc = ldexp(1.0, -21) * std::max(5.0 * b_max, 8.0);
+  // distance a_m + b_j - 2 <x, X_j> (three split-fp16 Gram products ~2^-22 each, fp32 adds: one fp32 unit round-off,
+  // 2^-24, of a_m + b_j as the standard deviation; the product |phi'(acc)| (a_m + b_j) is bounded over ALL candidates
+  // by K_phi max(5 b_max, 8), because far candidates have r ~ 0).  Measured on 25 000 float64-checked candidates per
+  // BASELINE workload the resulting dy sits 17-60 x above the largest yhat error (profiles/r02/band_probe.json).
+  const double e_acc = ldexp(1.0, -24) * std::max(5.0 * b_max, 8.0);
   double kphi = 0.6931471805599453;                       // RBF / abs-exp: d 2^-acc / d acc
   if (h->corr == MATERN32) kphi = 0.5;
   if (h->corr == MATERN52) kphi = 1.0 / 6.0;
@@ -1780,9 +1798,11 @@ static int run_candidates_fast(b200bo_handle h, const double* Xc, int64_t M, int
   }
 
   // ---- phase II / III: band selection + exact re-score, one stream-ordered pipeline per pass --------------------
-  const int BD = bd::BAND_DEV_MAX;
+  // on-device re-score up to BD band members: the row-sweep kernel costs ~ count x ld^2 / 2 fp64 MACs out of L2 / shared
+  // memory (fine for tens of candidates at N = 8192, for a thousand at N = 1024); wider bands take the tile kernels
+  const int BD = (int)std::max<long long>(32, std::min<long long>(bd::BAND_DEV_MAX, (5LL << 28) / ((long long)ld * ld) / 8 * 8));
   const int nslices = ld / bd::KSS_COLS + (ld % bd::KSS_COLS ? 1 : 0);
-  const int rd_grid = h->num_sms * 2, rd_warps = rd_grid * bd::RD_WARPS;
+  const int rd_blocks = ld / bd::RD_WARPS, rd_grid = std::min(rd_blocks, h->num_sms * 2);
   CU_TRY(h->thr_key.reserve(2 * (size_t)q));
   CU_TRY(h->band_list0.reserve(LIST0_CAP));
   CU_TRY(h->band_list.reserve(LIST0_CAP));
@@ -1791,7 +1811,7 @@ static int run_candidates_fast(b200bo_handle h, const double* Xc, int64_t M, int
   CU_TRY(h->Xband.reserve((size_t)Mc * D));
   CU_TRY(h->bd_kst.reserve((size_t)BD * ld));
   CU_TRY(h->bd_ypart.reserve((size_t)nslices * BD));
-  CU_TRY(h->bd_part.reserve((size_t)rd_warps * BD * 2));
+  CU_TRY(h->bd_part.reserve((size_t)rd_blocks * BD * 2));
   CU_TRY(h->bd_ctl.reserve(1));
   if (!h->pin) CU_TRY(cudaHostAlloc(&h->pin, PIN_BYTES, cudaHostAllocDefault));
   // pinned staging: [params q][BandCtl][best_val q][best_idx q]
@@ -1848,7 +1868,7 @@ static int run_candidates_fast(b200bo_handle h, const double* Xc, int64_t M, int
     rd.cap = BD; rd.ld = ld;
     bd::rowdot_kernel<<<rd_grid, 32 * bd::RD_WARPS, 0, st>>>(rd);
     CU_TRY(cudaGetLastError());
-    bd::band_moments_kernel<<<BD, 128, 0, st>>>(h->bd_ypart.p, nslices, h->bd_part.p, rd_warps, h->band_count.p + 1, BD, h->beta,
+    bd::band_moments_kernel<<<BD, 128, 0, st>>>(h->bd_ypart.p, nslices, h->bd_part.p, rd_blocks, h->band_count.p + 1, BD, h->beta,
                                                 h->yhat.p, h->sumsq.p, h->dotf.p);
     CU_TRY(cudaGetLastError());
     {
@@ -1972,8 +1992,21 @@ int b200bo_acq(b200bo_handle h, const double* Xc, int64_t M, int loc, int acq_id
   CHECK_ARG(q >= 1 && q <= 4096, "q out of range");
   CHECK_ARG(best_val && best_idx, "best_val / best_idx are NULL");
   CHECK_ARG(params || acq_id == B200BO_ACQ_EI, "params is NULL");
-  return run_candidates(h, Xc, M, loc, 1, nullptr, nullptr, acq_id, minimize, plugin, params, q, vals, best_val,
-                        best_idx);
+  int rc = run_candidates(h, Xc, M, loc, 1, nullptr, nullptr, acq_id, minimize, plugin, params, q, vals, best_val, best_idx);
+  if (!rc) h->last_q = q;
+  return rc;
+}
+
+int b200bo_best_pairs_device(b200bo_handle h, int64_t index_offset, int rank, int world, void* out_dev) {
+  CHECK_ARG(h && out_dev, "NULL argument");
+  CHECK_ARG(world >= 1 && rank >= 0 && rank < world, "bad rank / world");
+  if (h->last_q <= 0) return set_err(B200BO_E_STATE, "no acquisition call yet");
+  CU_TRY(cudaSetDevice(h->device));
+  const int n = world * 2 * h->last_q;
+  best_pairs_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(h->best_val.p, h->best_idx.p, h->last_q, index_offset, rank, world,
+                                                           (long long*)out_dev);
+  CU_TRY(cudaGetLastError());
+  return 0;
 }
 
 int b200bo_acq_from_moments(b200bo_handle h, const double* yhat, const double* mse, int64_t M, int loc, int acq_id,

@@ -23,7 +23,7 @@
 namespace b2 {
 namespace bd {
 
-constexpr int BAND_DEV_MAX = 256;  // widest band re-scored without a host round trip
+constexpr int BAND_DEV_MAX = 1024;  // capacity of the on-device re-score buffers (the host picks the cut-over per N)
 constexpr int KSS_COLS = 256;      // training columns per CTA of kstar_small_kernel
 constexpr int KSS_ROWS = 8;        // candidates per CTA of kstar_small_kernel
 constexpr int RD_WARPS = 16;       // warps per CTA of rowdot_kernel
@@ -134,76 +134,96 @@ __global__ void __launch_bounds__(KSS_COLS) kstar_small_kernel(KstarSmallArgs p)
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// rt = L^-1 r^T for a handful of candidates: ONE sweep over the lower triangle of L^-1 at HBM speed.
-// A warp owns rows n = w, w + W, w + 2 W, ... (interleaved: balanced triangle, fixed assignment => deterministic);
-// its lanes stride over k, so a row is read in 256-byte coalesced pieces with RD_UNROLL of them in flight per lane;
-// the candidates' r rows (a few tens of KB) come from L1 / L2.  Candidates are taken RD_CB at a time in registers
-// (a wider band re-sweeps the row, which by then sits in L1).  After the shuffle reduction lane c keeps candidate c's
-// running sums over the warp's rows; they go to part[(warp, candidate, 2)] and band_moments_kernel adds the warps'
-// partials in a fixed order.
+// rt = L^-1 r^T for a handful of candidates: sweeps over the lower triangle of L^-1 at memory speed.
+// A CTA owns 16 consecutive rows of L^-1 (one per warp: equal lengths inside the CTA; row blocks are dealt to the CTAs
+// round-robin); its lanes stride over k, so a row is read in 256-byte coalesced pieces, RD_UNROLL of them in flight
+// per lane and the next k-step's pieces requested before the current one is used.  The candidates' r rows are staged
+// RD_CB candidates x RD_KT columns at a time in shared memory and shared by the 16 warps (per-warp reads of r from
+// L2 made the first version of this kernel L2-bound: 0.4 ms for a 22-candidate band at N = 4096).  A wider band takes
+// further passes over the row block, which by then sits in L2.  Summation orders are fixed: lanes -> shuffle tree,
+// warps -> serial over the 16 rows, row blocks -> band_moments_kernel (bit-reproducible).
 // ---------------------------------------------------------------------------------------------------------------
+constexpr int RD_KT = 32 * RD_UNROLL;  // k columns per step
+
 struct RowdotArgs {
   const double* Kst;   // (cap, ld)
   const double* Linv;  // (ld, ld) lower
   const double* Ft;    // (ld,)
-  double* part;        // (total warps, cap, 2)
+  double* part;        // (ld / RD_WARPS, cap, 2): per row block [0] sum rt^2, [1] Ft . rt
   const int* count;
   int cap, ld;
 };
 
 __global__ void __launch_bounds__(32 * RD_WARPS) rowdot_kernel(RowdotArgs p) {
+  __shared__ double Ks[RD_CB][RD_KT];
+  __shared__ double red[2][RD_WARPS][RD_CB];
   const int m = min(*p.count, p.cap);
   if (m <= 0) return;
-  const int lane = threadIdx.x & 31;
-  const int gw = blockIdx.x * RD_WARPS + (threadIdx.x >> 5);
-  const int nw = gridDim.x * RD_WARPS;
-  for (int c0 = 0; c0 < m; c0 += 32) {  // 32 candidates per pass: lane c - c0 keeps candidate c's sums
-    double tot_ss = 0.0, tot_df = 0.0;
-    for (int n = gw; n < p.ld; n += nw) {
-      const double* wrow = p.Linv + (size_t)n * p.ld;
-      const double f = p.Ft[n];
-      for (int cb = c0; cb < min(m, c0 + 32); cb += RD_CB) {
-        double acc[RD_CB];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nblk = p.ld / RD_WARPS;
+  for (int rb = blockIdx.x; rb < nblk; rb += gridDim.x) {
+    const int n = rb * RD_WARPS + warp;          // this warp's row
+    const int nmax = rb * RD_WARPS + RD_WARPS - 1;
+    const double* wrow = p.Linv + (size_t)n * p.ld;
+    const double f = p.Ft[n];
+    for (int c0 = 0; c0 < m; c0 += RD_CB) {
+      double acc[RD_CB];
 #pragma unroll
-        for (int j = 0; j < RD_CB; ++j) acc[j] = 0.0;
-        for (int k0 = 0; k0 <= n; k0 += 32 * RD_UNROLL) {
-          double wv[RD_UNROLL];
+      for (int j = 0; j < RD_CB; ++j) acc[j] = 0.0;
+      double wv[RD_UNROLL], wn[RD_UNROLL];
+#pragma unroll
+      for (int u = 0; u < RD_UNROLL; ++u) {
+        const int k = 32 * u + lane;
+        wn[u] = k <= n ? wrow[k] : 0.0;
+      }
+      for (int k0 = 0; k0 <= nmax; k0 += RD_KT) {
+        __syncthreads();  // the previous tile has been consumed
+        for (int e = threadIdx.x; e < RD_CB * RD_KT; e += 32 * RD_WARPS) {
+          const int c = e / RD_KT, kk = e % RD_KT;
+          Ks[c][kk] = (c0 + c < m) ? p.Kst[(size_t)(c0 + c) * p.ld + k0 + kk] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < RD_UNROLL; ++u) wv[u] = wn[u];
+        if (k0 + RD_KT <= nmax) {
 #pragma unroll
           for (int u = 0; u < RD_UNROLL; ++u) {
-            const int k = k0 + 32 * u + lane;
-            wv[u] = k <= n ? wrow[k] : 0.0;
-          }
-#pragma unroll
-          for (int j = 0; j < RD_CB; ++j) {
-            if (cb + j < m) {  // warp-uniform
-              const double* kr = p.Kst + (size_t)(cb + j) * p.ld + k0 + lane;
-#pragma unroll
-              for (int u = 0; u < RD_UNROLL; ++u)
-                if (k0 + 32 * u <= n) acc[j] = fma(wv[u], kr[32 * u], acc[j]);  // k beyond n: wv = 0, kr stays inside the row (ld is a multiple of 128)
-            }
+            const int k = k0 + RD_KT + 32 * u + lane;
+            wn[u] = k <= n ? wrow[k] : 0.0;
           }
         }
+        __syncthreads();
 #pragma unroll
-        for (int j = 0; j < RD_CB; ++j) {
-          double v = acc[j];
+        for (int j = 0; j < RD_CB; ++j)
 #pragma unroll
-          for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-          if (lane == cb + j - c0) {
-            tot_ss = fma(v, v, tot_ss);
-            tot_df = fma(f, v, tot_df);
-          }
+          for (int u = 0; u < RD_UNROLL; ++u) acc[j] = fma(wv[u], Ks[j][32 * u + lane], acc[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < RD_CB; ++j) {
+        double v = acc[j];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) {
+          red[0][warp][j] = v * v;
+          red[1][warp][j] = f * v;
         }
       }
-    }
-    if (c0 + lane < m) {
-      double* o = p.part + ((size_t)gw * p.cap + c0 + lane) * 2;
-      o[0] = tot_ss;
-      o[1] = tot_df;
+      __syncthreads();
+      if (threadIdx.x < RD_CB && c0 + threadIdx.x < m) {
+        double a = 0.0, d = 0.0;
+#pragma unroll
+        for (int w = 0; w < RD_WARPS; ++w) {
+          a += red[0][w][threadIdx.x];
+          d += red[1][w][threadIdx.x];
+        }
+        double* o = p.part + ((size_t)rb * p.cap + c0 + threadIdx.x) * 2;
+        o[0] = a;
+        o[1] = d;
+      }
     }
   }
 }
 
-// yhat = beta + sum of the column-slice partials; sum rt^2, Ft^T rt = sum of the warps' partials (fixed orders)
+// yhat = beta + sum of the column-slice partials; sum rt^2, Ft^T rt = sum of the row blocks' partials (fixed orders)
 __global__ void band_moments_kernel(const double* __restrict__ ypart, int nslices, const double* __restrict__ part, int nwarps,
                                     const int* __restrict__ count, int cap, double beta, double* __restrict__ yhat,
                                     double* __restrict__ sumsq, double* __restrict__ dotf) {

@@ -78,3 +78,76 @@ def global_argmax(local_val: np.ndarray, local_idx: np.ndarray, offset: int, gro
         raise ValueError("collective should be 'allreduce' or 'allgather'")
     host = out.cpu().numpy().reshape(world, 2, q)
     return merge_argmax(host[:, 0].copy().view(np.float64), host[:, 1])
+
+
+class ArgmaxExchange:
+    """The global arg-max exchange with the host out of the data path, pipelined one step deep.
+
+    ``submit(engine, offset)`` (right after ``engine.acq``) has the engine write this rank's pairs into its row of a
+    (world, 2q) int64 block ON THE DEVICE (``b200bo_best_pairs_device``, ordered on the engine's stream), enqueues ONE
+    ``all_reduce(SUM)`` of the block (NCCL over NVLink; gloo on CPU tensors in the tests) and an asynchronous copy of the
+    reduced block into pinned host memory, and returns a ticket at once -- the next step's kernels can be launched
+    before the exchange of this one has run.  ``ticket.result()`` waits for that copy and merges the (world, q) pairs
+    with numpy's rule.  Two blocks alternate, so one exchange may be in flight while the next is submitted."""
+
+    def __init__(self, q: int, device=None, group=None):
+        import torch
+        import torch.distributed as dist
+
+        self.q, self.group = int(q), group
+        self.dist_on = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        self.world = dist.get_world_size(group) if self.dist_on else 1
+        self.rank = dist.get_rank(group) if self.dist_on else 0
+        self.device = torch.device("cpu") if device is None else torch.device(device)
+        self.cuda = self.device.type == "cuda"
+        self.blocks = [torch.zeros(self.world, 2 * self.q, dtype=torch.int64, device=self.device) for _ in range(2)]
+        self.host = [torch.zeros(self.world, 2 * self.q, dtype=torch.int64, pin_memory=self.cuda) for _ in range(2)]
+        self.turn = 0
+        self.done = [None, None]
+        # the collective and the copy back run on a high-priority side stream: the compute stream goes straight on to
+        # the next step's kernel instead of waiting for the slowest rank's contribution
+        self.side = torch.cuda.Stream(self.device, priority=-1) if self.cuda else None
+
+    class Ticket:
+        def __init__(self, ex, slot, event):
+            self.ex, self.slot, self.event = ex, slot, event
+
+        def result(self):
+            if self.event is not None:
+                self.event.synchronize()
+            h = self.ex.host[self.slot].numpy().reshape(self.ex.world, 2, self.ex.q)
+            return merge_argmax(h[:, 0].copy().view(np.float64), h[:, 1].copy())
+
+    def submit(self, engine=None, offset: int = 0, local_val=None, local_idx=None):
+        """pairs from the engine's device buffers (``engine`` given), or from host arrays (CPU tests, gloo)"""
+        import torch
+        import torch.distributed as dist
+
+        slot, self.turn = self.turn, self.turn ^ 1
+        blk = self.blocks[slot]
+        if self.done[slot] is not None:
+            self.done[slot].synchronize()   # the exchange that used this block two submits ago has been read
+        if engine is not None and self.cuda:
+            engine.best_pairs_device(blk, offset, self.rank, self.world)
+        else:
+            gidx = np.where(local_idx >= 0, local_idx + offset, -1).astype(np.int64)
+            row = np.concatenate([np.ascontiguousarray(local_val, dtype=np.float64).view(np.int64), gidx])
+            blk.zero_()
+            blk[self.rank] = torch.from_numpy(row).to(self.device)
+        if not self.cuda:
+            if self.dist_on:
+                dist.all_reduce(blk, op=dist.ReduceOp.SUM, group=self.group)   # gloo: blocking
+            self.host[slot].copy_(blk)
+            return ArgmaxExchange.Ticket(self, slot, None)
+        cur = torch.cuda.current_stream(self.device)
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        self.side.wait_event(ready)
+        with torch.cuda.stream(self.side):
+            if self.dist_on:
+                dist.all_reduce(blk, op=dist.ReduceOp.SUM, group=self.group)   # NCCL: stream-ordered on the side stream
+            self.host[slot].copy_(blk, non_blocking=True)
+            event = torch.cuda.Event()
+            event.record(self.side)
+        self.done[slot] = event
+        return ArgmaxExchange.Ticket(self, slot, event)

@@ -170,6 +170,13 @@ int b200bo_acq(b200bo_handle h, const double* Xc, int64_t M, int loc, int acq_id
                double plugin, const double* params, int q, double* vals, double* best_val,
                int64_t* best_idx);
 
+/* Multi-GPU arg-max exchange without the host: after b200bo_acq, write this rank's q (value,
+ * global index) pairs into row `rank` of a (world, 2 q) int64 block in DEVICE memory -- [value bits x q | index +
+ * index_offset x q, -1 for an empty shard] -- and zeros into the other rows, stream-ordered on the handle's stream.  One
+ * integer-sum ncclAllReduce of the block then delivers every rank's pairs bit for bit (each element has a single non-zero
+ * contributor); the caller merges them with numpy's rule.  Replaces the joblib fan-out of bayes_opt.py:108-111. */
+int b200bo_best_pairs_device(b200bo_handle h, int64_t index_offset, int rank, int world, void* out_dev);
+
 /* acquisition values from given (yhat, mse) -- the elementwise kernel alone (host or device pointers) */
 int b200bo_acq_from_moments(b200bo_handle h, const double* yhat, const double* mse, int64_t M, int loc,
                             int acq_id, int minimize, double plugin, const double* params, int q,

@@ -76,6 +76,14 @@ lv2 = np.array([-1.5 - rank, np.nan if rank == 1 else 2.0, 0.0])
 li2 = np.array([3, 4, -1 if rank == 0 else 5], dtype=np.int64)
 bv, bi = sharded.global_argmax(lv2, li2, 100 * rank)
 assert bv[0] == -1.5 and bi[0] == 3 and np.isnan(bv[1]) and bi[1] == 104 and bi[2] == 105, (bv, bi)
+# the pipelined exchange (two tickets in flight) gives the same merges
+ex = sharded.ArgmaxExchange(3)
+t1 = ex.submit(local_val=lv, local_idx=li, offset=lo)
+t2 = ex.submit(local_val=lv2, local_idx=li2, offset=100 * rank)
+bv, bi = t1.result()
+assert list(bi) == [int(np.argmax(x[c])) for c in range(3)] and list(bv) == [x[c].max() for c in range(3)]
+bv, bi = t2.result()
+assert bv[0] == -1.5 and bi[0] == 3 and np.isnan(bv[1]) and bi[1] == 104 and bi[2] == 105, (bv, bi)
 dist.destroy_process_group()
 print("OK", rank)
 """
