@@ -62,6 +62,7 @@ SIGNATURES = {
                                 C.c_int, C.c_void_p, _dp, _dp, _dp, _ip]),
     "b200bo_factor_restricted": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int,
                                            C.c_void_p, _dp, _ip]),
+    "b200bo_append": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, _dp, _dp, _dp, _ip]),
     "b200bo_llf_grad_restricted": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "b200bo_llf_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "b200bo_get_state": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
@@ -206,6 +207,18 @@ class Engine:
             self._h, int(corr), theta.ctypes.data, int(theta.size), float(sigma2), float(noise_var), int(trend),
             None if b is None else b.ctypes.data, C.byref(llf), C.byref(st)))
         return llf.value, st.value
+
+    def append(self, X_new, y_all):
+        """m new training points at the parameters of the last factor(): -> (llf, sigma2, noise_var, status)"""
+        X_new = _f64(X_new)
+        y_all = _f64(y_all).ravel()
+        if X_new.ndim != 2 or X_new.shape[1] != self.D or y_all.size != self.N + X_new.shape[0]:
+            raise ValueError("X_new must be (m, D) and y_all (N + m,)")
+        llf, s2, nv, st = C.c_double(), C.c_double(), C.c_double(), C.c_int()
+        _check(self._lib.b200bo_append(self._h, X_new.ctypes.data, int(X_new.shape[0]), y_all.ctypes.data, C.byref(llf),
+                                       C.byref(s2), C.byref(nv), C.byref(st)))
+        self.N += int(X_new.shape[0])
+        return llf.value, s2.value, nv.value, st.value
 
     def llf_grad_restricted(self, n_par: int) -> np.ndarray:
         g = np.empty(n_par)

@@ -223,6 +223,9 @@ struct b200bo_ctx {
   double last_err_y = 0, last_err_s = 0, last_ratio = 0;
   fk::BandArgs last_band{};
   LastFast last_fast;
+  std::vector<double> last_theta;  // arguments of the last factor(): b200bo_append re-uses them
+  double last_noise_arg = 0, last_beta_fixed = NAN;
+  DevBuf<double> ap_Tr, ap_Ts, ap_Tu, ap_Cb, ap_Dv;
   int last_q = 0;                 // criteria of the last acquisition call (b200bo_best_pairs_device)
   int dev_chunk_tiles = 0;        // B200BO_DEV_CHUNK_TILES: fused launches of this many tiles per SM on device-resident input
   std::vector<double> Xhost;      // training set as given (N, D): the distance-error bound needs max_j ||x_j||^2 per theta
@@ -415,6 +418,7 @@ int b200bo_destroy(b200bo_handle h) {
   h->trace.release(); h->errout.release(); h->band_list.release(); h->band_list0.release(); h->thr_key.release();
   h->band_count.release(); h->err_flag.release();
   h->Xall.release(); h->f_mse.release(); h->bd_kst.release(); h->bd_ypart.release(); h->bd_part.release();
+  h->ap_Tr.release(); h->ap_Ts.release(); h->ap_Tu.release(); h->ap_Cb.release(); h->ap_Dv.release();
   h->pm_v.release(); h->pm_t.release(); h->pm_t2.release(); h->rowsq.release(); h->rowl1.release(); h->bd_ctl.release();
   if (h->pin) cudaFreeHost(h->pin);
   for (int i = 0; i < 2; ++i) {
@@ -519,9 +523,14 @@ int b200bo_set_train(b200bo_handle h, const double* X, const double* y, int N, i
   return 0;
 }
 
+static int append_front(b200bo_handle h, int N0, int m, int corr, int mode, double par_last, double noise_var, int& launches);
+
+// append_m > 0: rows append_N0 .. append_N0 + append_m - 1 are new; A and W hold the factor of the leading block and steps
+// 1-3 (assembly, Cholesky, L^-1) are replaced by the bordering update of append_front
 static int factor_impl(b200bo_handle h, int corr, const double* theta, int n_theta, int mode, double par_last,
                        double noise_var, int trend, const double* beta_or_null, double* out_llf,
-                       double* out_sigma2, double* out_noise_var, int* out_status, bool restricted) {
+                       double* out_sigma2, double* out_noise_var, int* out_status, bool restricted,
+                       int append_N0 = 0, int append_m = 0) {
   CHECK_ARG(h && theta, "NULL argument");
   CHECK_ARG(h->N > 0, "set_train first");
   CHECK_ARG(corr >= 0 && corr <= 7, "unknown correlation id");
@@ -572,6 +581,12 @@ static int factor_impl(b200bo_handle h, int corr, const double* theta, int n_the
   cudaEvent_t e0 = h->evs.get(), e1 = h->evs.get();
   CU_TRY(cudaEventRecord(e0, st));
 
+  if (append_m > 0) {
+    pt.begin(0);
+    int rc = append_front(h, append_N0, append_m, corr, mode, par_last, noise_var, launches);
+    if (rc) return rc;
+    pt.end(0);
+  } else {
   // ---- 1. kernel-matrix assembly -------------------------------------------------------------------
   pt.begin(0);
   {
@@ -762,6 +777,7 @@ static int factor_impl(b200bo_handle h, int corr, const double* theta, int n_the
     if (rc) return rc;
   }
   pt.end(2);
+  }  // full factorisation
 
   // ---- 4. solves: Yt, Ft, rho, gamma and the likelihood scalars ---------------------------------------
   pt.begin(3);
@@ -881,6 +897,9 @@ static int factor_impl(b200bo_handle h, int corr, const double* theta, int n_the
   if (flag || llf != llf) status = B200BO_FIT_NOT_SPD;
   else if (llf > 0) status = B200BO_FIT_REJECTED;  // gpr.py:981-982
   h->restricted = restricted;
+  h->last_theta.assign(theta, theta + n_theta + (corr_has_extra_param(corr) ? 1 : 0));
+  h->last_noise_arg = noise_var;
+  h->last_beta_fixed = est ? NAN : beta_fixed;
   h->corr = corr; h->mode = mode; h->trend = trend; h->estimate_trend = est; h->n_theta = n_theta;
   h->par_last = par_last;
   h->sigma2 = s2; h->noise_var = nv;
@@ -894,6 +913,127 @@ static int factor_impl(b200bo_handle h, int corr, const double* theta, int n_the
   if (out_noise_var) *out_noise_var = nv;
   if (out_status) *out_status = status;
   return 0;
+}
+
+// ---- bordering update: [[R11, .], [R21, R22]] = [[L11, 0], [S, L22]] [[L11, 0], [S, L22]]^T with S = R21 L11^-T,
+// L22 L22^T = R22 - S S^T, and the new rows of the inverse [-L22^-1 S L11^-1 | L22^-1].  m <= 64 new points: three thin
+// DMMA GEMMs against L^-1 (2 x 64 N0^2 flops each) instead of the N^3 / 3 + N^3 / 3 of a fresh factor + inverse.
+static int append_front(b200bo_handle h, int N0, int m, int corr, int mode, double par_last, double noise_var, int& launches) {
+  cudaStream_t st = h->stream;
+  const int ld = h->ld, D = h->D;
+  const int N0p = round_up(N0, NB);
+  CU_TRY(h->ap_Tr.reserve((size_t)NB * ld));
+  CU_TRY(h->ap_Ts.reserve((size_t)NB * ld));
+  CU_TRY(h->ap_Tu.reserve((size_t)NB * ld));
+  CU_TRY(h->ap_Cb.reserve((size_t)NB * NB));
+  CU_TRY(h->ap_Dv.reserve((size_t)NB * NB));
+  AppendRowsArgs a;
+  a.Xt = h->Xt.p; a.theta = h->theta.p; a.Tr = h->ap_Tr.p; a.Cb = h->ap_Cb.p;
+  a.N0 = N0; a.m = m; a.D = D; a.ld = ld; a.corr = corr; a.mode = mode;
+  a.sigma2 = mode == B200BO_MODE_NOISY ? par_last : 0.0;
+  a.noise_var = mode == B200BO_MODE_NOISY ? noise_var : 0.0;
+  a.alpha = mode == B200BO_MODE_NOISE_ESTIM ? par_last : 1.0;
+  const size_t smem = ((size_t)NB * D + D + 1) * sizeof(double);
+  if (smem > 48 * 1024) CU_TRY(cudaFuncSetAttribute(kmat_append_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kmat_append_rows_kernel<<<(ld + 255) / 256, 256, smem, st>>>(a);
+  CU_TRY(cudaGetLastError());
+  append_sym_kernel<<<(NB * NB + 255) / 256, 256, 0, st>>>(h->ap_Cb.p, m);
+  CU_TRY(cudaGetLastError());
+  // S(i, n) = sum_{k <= n} R21(i, k) W(n, k)
+  GemmArgs g{};
+  g.A = h->ap_Tr.p; g.lda = ld; g.B = h->W.p; g.ldb = ld; g.C = h->ap_Ts.p; g.ldc = ld;
+  g.K = N0p; g.alpha = 1.0; g.beta = 0.0; g.ke_mode = 1;
+  CU_TRY((launch_gemm<GemmNT, false, false>(h, g, NB, N0p, 1)));
+  // C22 <- R22 - S S^T, then its factor and the factor's inverse
+  GemmArgs c{};
+  c.A = h->ap_Ts.p; c.lda = ld; c.B = h->ap_Ts.p; c.ldb = ld; c.C = h->ap_Cb.p; c.ldc = NB;
+  c.K = N0p; c.alpha = -1.0; c.beta = 1.0;
+  CU_TRY((launch_gemm<GemmNT, false, false>(h, c, NB, NB, 1)));
+  CU_TRY(cudaFuncSetAttribute(chol_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHOL_FACTOR_SMEM));
+  CU_TRY(cudaFuncSetAttribute(chol_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHOL_DIAG_SMEM));
+  chol_factor_kernel<<<1, 256, CHOL_FACTOR_SMEM, st>>>(h->ap_Cb.p, NB, h->status.p);
+  CU_TRY(cudaGetLastError());
+  chol_inverse_kernel<<<1, 256, CHOL_DIAG_SMEM, st>>>(h->ap_Cb.p, NB, h->ap_Dv.p);
+  CU_TRY(cudaGetLastError());
+  // U(i, n) = sum_{k >= n} S(i, k) W(k, n);  W21 = -L22^-1 U
+  GemmArgs u{};
+  u.A = h->ap_Ts.p; u.lda = ld; u.B = h->W.p; u.ldb = ld; u.C = h->ap_Tu.p; u.ldc = ld;
+  u.K = N0p; u.alpha = 1.0; u.beta = 0.0; u.kb_mode = 1;
+  CU_TRY((launch_gemm<GemmNN, false, true>(h, u, NB, N0p, 1)));
+  GemmArgs w{};
+  w.A = h->ap_Dv.p; w.lda = NB; w.B = h->ap_Tu.p; w.ldb = ld; w.C = h->ap_Tr.p; w.ldc = ld;
+  w.K = NB; w.alpha = -1.0; w.beta = 0.0;
+  CU_TRY((launch_gemm<GemmNN, false, true>(h, w, NB, N0p, 1)));
+  append_scatter_kernel<<<(ld + 255) / 256, 256, 0, st>>>(h->A.p, h->W.p, ld, N0, m, h->ap_Ts.p, h->ap_Tr.p, h->ap_Cb.p, h->ap_Dv.p);
+  CU_TRY(cudaGetLastError());
+  launches += 9;
+  return 0;
+}
+
+int b200bo_append(b200bo_handle h, const double* X_new, int m_total, const double* y_all, double* out_llf, double* out_sigma2,
+                  double* out_noise_var, int* out_status) {
+  CHECK_ARG(h && X_new && y_all, "NULL argument");
+  CHECK_ARG(m_total >= 1, "m must be positive");
+  if (!h->factored) return set_err(B200BO_E_STATE, "append before a successful factor()");
+  CHECK_ARG(h->trend == B200BO_TREND_CONSTANT, "append is implemented for the constant trend");
+  CU_TRY(cudaSetDevice(h->device));
+  const int D = h->D;
+  const std::vector<double> theta = h->last_theta;
+  const int n_theta_arg = (int)theta.size();
+  const int corr = h->corr, mode = h->mode, trend = h->trend;
+  const double par_last = h->par_last, noise_arg = h->last_noise_arg;
+  const bool restricted = h->restricted;
+  const bool est = h->estimate_trend != 0;
+  const double beta_fixed = h->last_beta_fixed;
+  int rc = 0;
+  for (int done = 0; done < m_total && !rc; done += NB) {
+    const int m = std::min(NB, m_total - done);
+    const int N0 = h->N, N1 = N0 + m, ld0 = h->ld, ld1 = round_up(N1, 128);
+    cudaStream_t st = h->stream;
+    // ---- training set: host copy, transposed device copy (new pitch when ld grows), targets -----------------------
+    h->Xhost.insert(h->Xhost.end(), X_new + (size_t)done * D, X_new + (size_t)(done + m) * D);
+    std::vector<double> xt((size_t)D * ld1, 0.0), yy(ld1, 0.0), ff(ld1, 0.0);
+    h->xmean.assign(D, 0.0);
+    for (int i = 0; i < N1; ++i)
+      for (int d = 0; d < D; ++d) {
+        const double v = h->Xhost[(size_t)i * D + d];
+        xt[(size_t)d * ld1 + i] = v;
+        h->xmean[d] += v;
+      }
+    for (int d = 0; d < D; ++d) h->xmean[d] /= N1;
+    // the targets of the rows not appended yet are not part of this step's model
+    for (int i = 0; i < N1; ++i) {
+      yy[i] = y_all[i];
+      ff[i] = 1.0;
+    }
+    CU_TRY(h->Xt.reserve(xt.size()));
+    CU_TRY(h->y.reserve(ld1));
+    CU_TRY(h->F.reserve(ld1));
+    CU_TRY(cudaMemcpyAsync(h->Xt.p, xt.data(), xt.size() * 8, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(h->y.p, yy.data(), (size_t)ld1 * 8, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(h->F.p, ff.data(), (size_t)ld1 * 8, cudaMemcpyHostToDevice, st));
+    if (ld1 != ld0) {
+      // the pitch changes: move L and L^-1 into larger buffers (identity on the new padding)
+      DevBuf<double> nA, nW;
+      CU_TRY(nA.reserve((size_t)ld1 * ld1));
+      CU_TRY(nW.reserve((size_t)ld1 * ld1));
+      grow_matrix_kernel<<<h->num_sms * 8, 256, 0, st>>>(h->A.p, ld0, nA.p, ld1, N0);
+      grow_matrix_kernel<<<h->num_sms * 8, 256, 0, st>>>(h->W.p, ld0, nW.p, ld1, N0);
+      CU_TRY(cudaGetLastError());
+      CU_TRY(cudaStreamSynchronize(st));
+      h->A.release(); h->W.release(); h->S.release();
+      h->A = nA; h->W = nW;
+      h->Kst.release();
+      h->g_chol.drop(); h->g_trtri.drop();
+    }
+    CU_TRY(cudaStreamSynchronize(st));  // xt / yy / ff are stack-owned
+    h->N = N1;
+    h->ld = ld1;
+    rc = factor_impl(h, corr, theta.data(), n_theta_arg, mode, par_last, noise_arg, trend, est ? nullptr : &beta_fixed, out_llf,
+                     out_sigma2, out_noise_var, out_status, restricted, N0, m);
+    if (!rc && out_status && *out_status != B200BO_FIT_OK) break;
+  }
+  return rc;
 }
 
 int b200bo_factor(b200bo_handle h, int corr, const double* theta, int n_theta, int mode, double par_last,

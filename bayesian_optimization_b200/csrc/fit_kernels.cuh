@@ -106,6 +106,94 @@ __global__ void __launch_bounds__(256) kmat_assemble_kernel(AssembleArgs p) {
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Appending m <= 64 training points to a factored model (b200bo_append): the m new ROWS of R, mode scaling as
+// in kmat_assemble_kernel.  Columns j < N0 (correlations with the old points) go to Tr (64, ld), zero-padded;
+// the (m, m) block among the new points goes to Cb (64, 64) with an identity pad.  grid = ld / 256, 256 threads.
+// ---------------------------------------------------------------------------------------------------
+struct AppendRowsArgs {
+  const double* Xt;     // (D, ld), already holding the new points in columns N0 .. N0 + m - 1
+  const double* theta;  // (D [+1])
+  double* Tr;           // (64, ld)
+  double* Cb;           // (64, 64)
+  int N0, m, D, ld, corr, mode;
+  double sigma2, noise_var, alpha;
+};
+
+__global__ void __launch_bounds__(256) kmat_append_rows_kernel(AppendRowsArgs p) {
+  extern __shared__ __align__(16) double sm_ar[];
+  double* xn = sm_ar;              // [64][D] new points
+  double* th = xn + NB * p.D;      // [D]
+  const int tid = threadIdx.x;
+  for (int e = tid; e < NB * p.D; e += 256) {
+    const int i = e / p.D, d = e % p.D;
+    xn[e] = i < p.m ? p.Xt[(size_t)d * p.ld + p.N0 + i] : 0.0;
+  }
+  for (int d = tid; d < p.D; d += 256) th[d] = p.theta[d];
+  const double pw = corr_has_extra_param(p.corr) ? p.theta[p.D] : 0.0;
+  __syncthreads();
+  const int j = blockIdx.x * 256 + tid;  // column of R
+  if (j >= p.ld) return;
+  const double s2t = p.sigma2 + p.noise_var;
+  const double diag = p.mode == 1 ? (p.sigma2 + p.noise_var) / s2t : (p.mode == 2 ? p.alpha + (1.0 - p.alpha) : 1.0);
+  for (int i = 0; i < NB; ++i) {
+    const int gi = p.N0 + i;
+    double v = 0.0;
+    if (i < p.m && j <= gi) {
+      if (j == gi) {
+        v = diag;
+      } else {
+        double acc = corr_init(p.corr);
+        for (int d = 0; d < p.D; ++d) acc = corr_accum_p(p.corr, acc, th[d], xn[i * p.D + d] - p.Xt[(size_t)d * p.ld + j], pw);
+        const double r = corr_finish_p(p.corr, acc, pw);
+        v = p.mode == 1 ? (p.sigma2 * r) / s2t : (p.mode == 2 ? p.alpha * r : r);
+      }
+    }
+    if (j < p.N0) p.Tr[(size_t)i * p.ld + j] = v;
+    else p.Tr[(size_t)i * p.ld + j] = 0.0;
+    const int c = j - p.N0;
+    if (c >= 0 && c < NB) p.Cb[i * NB + c] = (i < p.m && c < p.m) ? (c <= i ? v : 0.0) : (i == c ? 1.0 : 0.0);
+  }
+}
+
+// symmetrise the (64, 64) block before its Cholesky update (the GEMM S S^T fills every entry; only the lower part of
+// the R block was written)
+__global__ void append_sym_kernel(double* __restrict__ Cb, int m) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= NB * NB) return;
+  const int i = e / NB, c = e % NB;
+  if (c > i && i < m && c < m) Cb[e] = Cb[c * NB + i];
+}
+
+// rows N0 .. N0 + m - 1 of L and L^-1 from the pieces: [S | L22 | 0] and [W21 | L22^-1 | 0]
+__global__ void __launch_bounds__(256) append_scatter_kernel(double* __restrict__ A, double* __restrict__ W, int ld, int N0, int m,
+                                                             const double* __restrict__ S, const double* __restrict__ W21,
+                                                             const double* __restrict__ L22, const double* __restrict__ L22inv) {
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  if (j >= ld) return;
+  for (int i = 0; i < m; ++i) {
+    double a = 0.0, w = 0.0;
+    if (j < N0) {
+      a = S[(size_t)i * ld + j];
+      w = W21[(size_t)i * ld + j];
+    } else if (j - N0 <= i) {
+      a = L22[i * NB + (j - N0)];
+      w = L22inv[i * NB + (j - N0)];
+    }
+    A[(size_t)(N0 + i) * ld + j] = a;
+    W[(size_t)(N0 + i) * ld + j] = w;
+  }
+}
+
+// new (ld1, ld1) buffer from an (ld0, ld0) one: the leading (n, n) block is copied, the rest is the identity
+__global__ void grow_matrix_kernel(const double* __restrict__ src, int ld0, double* __restrict__ dst, int ld1, int n) {
+  const size_t total = (size_t)ld1 * ld1;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(e / ld1), j = (int)(e % ld1);
+    dst[e] = (i < n && j < n) ? src[(size_t)i * ld0 + j] : (i == j ? 1.0 : 0.0);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Diagonal block: factor A[jb,jb] = Ljj Ljj^T in shared memory, write Ljj back (lower; the strict upper
 // triangle of the block is zeroed) and its inverse to Dinv (64x64 row-major, zero strict upper).
 // status[0] |= 1 when a pivot is <= 0 or NaN (scipy.linalg.cholesky raises LinAlgError there, gpr.py:795).

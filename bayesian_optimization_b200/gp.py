@@ -421,9 +421,42 @@ class GaussianProcess:
         self._adopt(self.par["theta"], last, env)
         return self
 
-    def update(self, X, y):
-        self.fit(X, y)  # gpr.py:419-422
-        return self
+    def update(self, X, y, reoptimize: bool = True):
+        """``update(X, y)`` is ``fit(X, y)`` upstream, with a "TODO: implement the rank-one update" next to it
+        (gpr.py:419-422); that stays the default.  ``reoptimize=False`` keeps the hyper-parameters and, when ``X`` is
+        the current training set followed by new rows, APPENDS those rows to the factorisation on the device
+        (``b200bo_append``: O(m N^2) instead of O(N^3)); ``y`` holds every target (BaseBO re-standardises them whenever a
+        point arrives, base.py:437).  Anything else -- reordered rows, a trend with p > 1, several targets, a failed
+        update -- falls back to a fixed-parameter refit, then to ``fit``."""
+        if reoptimize or not self.is_fitted or self._sub or getattr(self, "_trend_id", 0) != _lib.TREND_CONSTANT:
+            return self.fit(X, y)
+        Xn, yn = check_X_y(X, y, multi_output=True, y_numeric=True)
+        yn = yn.reshape(len(yn), -1)
+        if yn.shape[1] != 1:
+            return self.fit(X, y)
+        N0, D = self.X.shape
+        Xn = np.ascontiguousarray(Xn, dtype=np.float64)
+        appendable = (Xn.shape[1] == D and Xn.shape[0] > N0 and np.array_equal(Xn[:N0], self.X) and self._engine is not None
+                      and self._engine.N == N0)
+        if appendable:
+            llf, s2, nv, status = self._engine.append(Xn[N0:], yn[:, 0])
+            if status == _lib.FIT_OK:
+                self.X, self.y = Xn, np.ascontiguousarray(yn, dtype=np.float64)
+                self._cache = {}
+                self._train_gen += 1
+                self.log_likelihood_ = llf
+                if self.estimate_trend:
+                    self.F = self.mean.F(self.X)
+                env = {"sigma2": np.atleast_1d(s2), "noise_var": nv}
+                if self.likelihood == "restricted":
+                    env = {"sigma2": self._restricted_par[0], "noise_var": self._restricted_par[1]}
+                self._adopt(self.theta_, self._par_last, env)
+                return self
+        if self.likelihood == "restricted":
+            llf = self.fit_fixed_restricted(Xn, yn, self.theta_, self._restricted_par[0], self._restricted_par[1])
+        else:
+            llf = self.fit_fixed(Xn, yn, self.theta_, self._par_last)
+        return self if np.isfinite(llf) else self.fit(X, y)
 
     # ---- lazily fetched state ------------------------------------------------------------------------
     def _state(self, key, what, shape=None):

@@ -150,6 +150,16 @@ int b200bo_factor_restricted(b200bo_handle h, int corr, const double* theta, int
  * the reference indexes its gradient tensor by the PARAMETER number, also for an isotropic theta. */
 int b200bo_llf_grad_restricted(b200bo_handle h, double* out_grad, int n_par);
 
+/* -- GaussianProcess.update(X, y) with the hyper-parameters kept: the bordering ("rank-m") update upstream left as a TODO
+ * (gpr.py:419-422 "TODO: implement the rank-one update").  Appends m new training points X_new (m, D) to the model of
+ * the last b200bo_factor / b200bo_factor_restricted call at the SAME parameters: new rows of L and of L^-1 from three
+ * thin GEMMs against L^-1 (O(m N^2)) instead of a fresh N^3 factorisation, then Yt, Ft, rho, gamma, beta, sigma2 and
+ * the likelihood for y_all (N + m,) -- every target, because the callers re-standardise y whenever a point is added
+ * (base.py:437).  The state afterwards equals set_train(X_all, y_all) + factor(same parameters) to rounding
+ * (tests/test_update_gpu.py: likelihood 1e-10, posterior 1e-9).  Constant trend; any m (blocks of 64). */
+int b200bo_append(b200bo_handle h, const double* X_new, int m, const double* y_all, double* out_llf, double* out_sigma2,
+                  double* out_noise_var, int* out_status);
+
 int b200bo_get_state(b200bo_handle h, int what, double* out, size_t n_elems);
 
 /* -- GaussianProcess.predict(X, eval_MSE) (gpr.py:424-512) --------------------------------------------

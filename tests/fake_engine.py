@@ -46,12 +46,18 @@ class FakeEngine:
         elif mode == go.MODE_NOISE_ESTIM:
             kw.update(alpha=par_last)
         gp = go.fit_fixed(self.X, self.y, corr, theta, mode, **kw)
+        self._last = (corr, np.array(theta, dtype=np.float64), mode, par_last, noise_var, trend, beta)
         self.restricted = False
         if not np.isfinite(gp.llf):
             self.gp = None
             return -np.inf, np.nan, np.nan, _lib.FIT_REJECTED
         self.gp, self._alpha = gp, (par_last if mode == go.MODE_NOISE_ESTIM else None)
         return gp.llf, gp.sigma2, gp.noise_var, _lib.FIT_OK
+
+    def append(self, X_new, y_all):
+        corr, theta, mode, par_last, noise_var, trend, beta = self._last
+        self.set_train(np.vstack([self.X, np.asarray(X_new, dtype=np.float64)]), y_all)
+        return self.factor(corr, theta, mode, par_last, noise_var, trend, beta)
 
     def llf_grad(self, n_par):
         return np.asarray(go.llf_grad(self.gp, self._alpha), dtype=np.float64).ravel()[:n_par]

@@ -249,3 +249,32 @@ def test_concurrent_restarts_equal_the_sequential_loop(name, random_start, eval_
     assert a.log_likelihood_ == pytest.approx(llf, rel=1e-12)
     np.testing.assert_allclose(np.r_[a.par["theta"], [a.par[k][0] for k in a.par if k != "theta"]], par, rtol=1e-12)
     assert state_a[0] == state_b[0] and np.array_equal(state_a[1], state_b[1]) and state_a[2:] == state_b[2:]
+
+
+def test_update_appends_rows_or_refits():
+    """update(X, y, reoptimize=False): new rows behind the current training set go through Engine.append (same state as
+    a fixed-parameter refit); reordered data falls back to that refit; the default stays upstream's update = fit"""
+    c = FITS["rbf_ny"]
+    D, mode, kw = _kwargs(c)
+    X, y = c["X"], c["y"]
+    n0 = X.shape[0] - 7
+    a = b2.GaussianProcess(mean=b2.constant_trend(D), **kw)
+    np.random.seed(3)
+    a.fit(X[:n0], y[:n0])
+    theta, last = a.theta_.copy(), a._par_last
+    calls = a.engine.n_factor
+    assert a.update(X, y, reoptimize=False) is a
+    assert a.engine.n_factor == calls + 1 and a.X.shape == X.shape and np.array_equal(a.theta_, theta)
+    ref = go.fit_fixed(X, y, int(c["corr"]), theta, mode, sigma2=last, noise_var=1e-2)
+    assert a.log_likelihood_ == pytest.approx(ref.llf, rel=1e-12)
+    np.testing.assert_allclose(a.predict(c["Xc"]), go.predict_chunked(ref, c["Xc"], 64, eval_MSE=False), rtol=1e-10)
+    # reordered rows: not an append, still the fixed-parameter model of the new data
+    b = b2.GaussianProcess(mean=b2.constant_trend(D), **kw)
+    np.random.seed(3)
+    b.fit(X[:n0], y[:n0])
+    b.update(X[::-1], y[::-1], reoptimize=False)
+    assert b.log_likelihood_ == pytest.approx(ref.llf, rel=1e-10) and np.array_equal(b.theta_, theta)
+    # default: upstream's update() re-estimates the hyper-parameters
+    np.random.seed(4)
+    b.update(X, y)
+    assert b.eval_count > 0
