@@ -113,12 +113,14 @@ __global__ void __launch_bounds__(KSS_COLS) kstar_small_kernel(KstarSmallArgs p)
       for (int r = 0; r < KSS_ROWS; ++r) acc[r] = corr_accum_p(p.corr, acc[r], thd, xc[r * p.D + d] - xd, pw);
     }
   }
-  const double g = p.gamma[n];
+  // the last column slice may reach past the pitch (ld is a multiple of 128, the slice is 256 wide): those threads
+  // only take part in the reductions
+  const double g = n < p.ld ? p.gamma[n] : 0.0;
   const int lane = tid & 31, w = tid >> 5;
 #pragma unroll
   for (int r = 0; r < KSS_ROWS; ++r) {
     const double k = n < p.N ? corr_finish_p(p.corr, acc[r], pw) : 0.0;
-    if (m0 + r < m) p.Kst[(size_t)(m0 + r) * p.ld + n] = k;
+    if (m0 + r < m && n < p.ld) p.Kst[(size_t)(m0 + r) * p.ld + n] = k;
     double v = k * g;
 #pragma unroll
     for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
