@@ -53,6 +53,8 @@ SIGNATURES = {
     "b200bo_set_fast_kernel": (C.c_int, [C.c_void_p, C.c_int]),
     "b200bo_set_fast_products": (C.c_int, [C.c_void_p, C.c_int]),
     "b200bo_set_replay": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "b200bo_set_chol_tc": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "b200bo_debug_oz_syrk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "b200bo_gradient": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200bo_acq_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_double, C.c_double,
                                   C.c_void_p, C.c_void_p]),
@@ -335,6 +337,21 @@ class Engine:
         _check(self._lib.b200bo_acq_grad(self._h, Xc.ctypes.data, M, int(acq_id), int(bool(minimize)), float(plugin),
                                          float(param), val.ctypes.data, dx.ctypes.data))
         return val, dx
+
+    def set_chol_tc(self, digits: int, min_rows: int = 0):
+        """Cholesky trailing updates on tcgen05 int8 digit planes (7 or 8), 0 = fp64 DMMA"""
+        _check(self._lib.b200bo_set_chol_tc(self._h, int(digits), int(min_rows)))
+
+    def debug_oz_syrk(self, P: np.ndarray, Cm: np.ndarray, digits: int = 8, reps: int = 1):
+        """C - P P^T on the lower tiles through the tensor-core (digits 7 / 8) or the DMMA (0) kernel; (C', best ms)"""
+        P = _f64(P)
+        out = np.array(Cm, dtype=np.float64, order="C", copy=True)
+        rows = P.shape[0]
+        if P.shape != (rows, 64) or out.shape != (rows, rows):
+            raise ValueError("P must be (rows, 64) and C (rows, rows)")
+        ms = C.c_double(0.0)
+        _check(self._lib.b200bo_debug_oz_syrk(self._h, P.ctypes.data, rows, out.ctypes.data, int(digits), int(reps), C.byref(ms)))
+        return out, ms.value
 
     def debug_fused_time(self, Xc: np.ndarray, products: int = 1, reps: int = 3) -> float:
         """average device ms of the fused tensor-core kernel alone (developer hook)"""

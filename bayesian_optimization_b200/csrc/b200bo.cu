@@ -24,6 +24,7 @@
 #include "fit_kernels.cuh"
 #include "grad_kernels.cuh"
 #include "host_qr.h"
+#include "oz_kernels.cuh"
 #include "predict_kernels.cuh"
 #include "trend_kernels.cuh"
 
@@ -232,6 +233,16 @@ struct b200bo_ctx {
   DevBuf<double> Xall, f_mse, bd_kst, bd_ypart, bd_part, pm_v, pm_t, pm_t2, rowsq, rowl1;
   DevBuf<bd::BandCtl> bd_ctl;
   uint8_t* pin = nullptr;         // pinned host staging of the band pipeline (parameters in, control block + bests out)
+  // Cholesky trailing update on the tcgen05 tensor cores (oz_kernels.cuh): int8 digit planes of the current panel
+  int chol_tc = 0;                // 0: fp64 DMMA trailing updates; 7 / 8: digit planes of the exact int8 splitting
+  int chol_tc_min_rows = 1024;    // smaller trailing matrices stay on the DMMA path (too few tiles to fill the SMs)
+  DevBuf<uint8_t> oz_dig;
+  DevBuf<double> oz_scA, oz_scB;
+  DevBuf<int> oz_err;
+  CUtensorMap oz_mapA, oz_mapB;
+  const void* oz_map_base = nullptr;
+  int oz_map_rcap = 0;
+  bool oz_attr = false;
 };
 
 namespace {
@@ -339,6 +350,94 @@ struct PhaseTimer {
   }
 };
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int get_encode_tiled(EncodeTiledFn* out) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CU_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres));
+    if (!f || qres != cudaDriverEntryPointSuccess) return set_err(B200BO_E_CUDA, "cuTensorMapEncodeTiled is not available");
+    fn = (EncodeTiledFn)f;
+  }
+  *out = fn;
+  return 0;
+}
+
+// generic 2-D row-major tensor map: `rows` rows of `inner` elements, row pitch in bytes, boxes of box_rows x box_inner
+static int make_map_2d(CUtensorMap* map, CUtensorMapDataType dt, const void* base, uint64_t inner, uint64_t rows,
+                       uint64_t pitch_bytes, int box_inner, int box_rows, CUtensorMapSwizzle sw) {
+  EncodeTiledFn fn;
+  int rc = get_encode_tiled(&fn);
+  if (rc) return rc;
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)pitch_bytes};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, dt, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_err(B200BO_E_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
+  return 0;
+}
+
+// ---- Cholesky trailing update on the tensor cores (oz_kernels.cuh) ---------------------------------------------------
+// C(r, c) -= sum_k P(r, k) P(c, k) over the lower tiles of the rows x rows matrix at C; P = rows x 64 panel (pitch ldp).
+// Two launches on `st`: the digit split of the panel, the tcgen05 int8 SYRK.  h->chol_tc = digit planes (7 or 8).
+static int launch_oz_syrk(b200bo_ctx* h, cudaStream_t st, const double* P, int ldp, int rows, double* C, int ldc,
+                          int& launches) {
+  const int S = h->chol_tc == 7 ? 7 : 8;
+  const int rows_pad = round_up(rows, oz::TM);
+  const int Rcap = std::max(h->ld, rows_pad);
+  CHECK_ARG(rows > 0 && rows % 64 == 0, "oz_syrk: the panel extent must be a positive multiple of 64");
+  CU_TRY(h->oz_dig.reserve((size_t)oz::NPL * Rcap * 128));
+  CU_TRY(h->oz_scA.reserve(Rcap));
+  CU_TRY(h->oz_scB.reserve(Rcap));
+  if (!h->err_flag.p) {
+    CU_TRY(h->err_flag.reserve(1));
+    CU_TRY(cudaMemsetAsync(h->err_flag.p, 0, sizeof(int), st));
+  }
+  int rc;
+  if (h->oz_map_base != h->oz_dig.p || h->oz_map_rcap != Rcap) {
+    if ((rc = make_map_2d(&h->oz_mapA, CU_TENSOR_MAP_DATA_TYPE_UINT8, h->oz_dig.p, 128, (uint64_t)oz::NPL * Rcap, 128, 128, oz::TM,
+                          CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    if ((rc = make_map_2d(&h->oz_mapB, CU_TENSOR_MAP_DATA_TYPE_UINT8, h->oz_dig.p, 128, (uint64_t)oz::NPL * Rcap, 128, 128, oz::TN,
+                          CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    h->oz_map_base = h->oz_dig.p;
+    h->oz_map_rcap = Rcap;
+  }
+  if (!h->oz_attr) {
+    CU_TRY(cudaFuncSetAttribute(oz::oz_syrk_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::SMEM_BYTES));
+    CU_TRY(cudaFuncSetAttribute(oz::oz_syrk_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::SMEM_BYTES));
+    h->oz_attr = true;
+  }
+  oz::OzArgs a;
+  a.scA = h->oz_scA.p; a.scB = h->oz_scB.p; a.C = C; a.ldc = ldc; a.rows = rows; a.Rcap = Rcap; a.err = h->err_flag.p;
+  a.dbg = getenv("B200BO_OZ_DEBUG") ? atoi(getenv("B200BO_OZ_DEBUG")) : 0;
+  const int ncb = (rows + oz::TM - 1) / oz::TM, nrb = rows / oz::TN;
+  long long tiles = 0;
+  for (int cb = 0; cb < ncb; ++cb) tiles += nrb - cb * (oz::TM / oz::TN);
+  a.G = (int)std::max<long long>(2, std::min<long long>(16, tiles / (2LL * h->num_sms)));
+  if (const char* e = getenv("B200BO_OZ_G")) a.G = std::max(1, atoi(e));
+  int items = 0;
+  for (int cb = 0; cb < ncb; ++cb) items += (nrb - cb * (oz::TM / oz::TN) + a.G - 1) / a.G;
+  const int grid = std::min(items, h->num_sms);
+  if (S == 7) {
+    oz::oz_split_kernel<7><<<rows_pad / 8, 256, 0, st>>>(P, ldp, rows, rows_pad, Rcap, h->oz_dig.p, h->oz_scA.p, h->oz_scB.p);
+    CU_TRY(cudaGetLastError());
+    oz::oz_syrk_kernel<7><<<grid, oz::NT_OZ, oz::SMEM_BYTES, st>>>(h->oz_mapA, h->oz_mapB, a);
+  } else {
+    oz::oz_split_kernel<8><<<rows_pad / 8, 256, 0, st>>>(P, ldp, rows, rows_pad, Rcap, h->oz_dig.p, h->oz_scA.p, h->oz_scB.p);
+    CU_TRY(cudaGetLastError());
+    oz::oz_syrk_kernel<8><<<grid, oz::NT_OZ, oz::SMEM_BYTES, st>>>(h->oz_mapA, h->oz_mapB, a);
+  }
+  CU_TRY(cudaGetLastError());
+  launches += 2;
+  return 0;
+}
+
 int ensure_predict_ws(b200bo_ctx* h, int q, bool need_vals_stage) {
   if (h->Mc == 0) h->Mc = h->num_sms * PC_BM;
   size_t Mc = h->Mc;
@@ -389,6 +488,8 @@ int b200bo_create(int device, b200bo_handle* out) {
   if (const char* e = getenv("B200BO_FAST_KERNEL")) h->fast_kernel_pref = std::max(1, std::min(5, atoi(e)));
   if (const char* e = getenv("B200BO_CHOL_LOOKAHEAD")) h->lookahead = std::max(0, std::min(2, atoi(e)));
   if (const char* e = getenv("B200BO_GRAPHS")) h->use_graphs = atoi(e) != 0;
+  if (const char* e = getenv("B200BO_CHOL_TC")) { int v = atoi(e); h->chol_tc = (v == 7 || v == 8) ? v : 0; }
+  if (const char* e = getenv("B200BO_CHOL_TC_MIN_ROWS")) h->chol_tc_min_rows = std::max(64, atoi(e));
   if (const char* e = getenv("B200BO_REPLAY_MB")) h->replay_mb = std::max(0, std::min(4096, atoi(e)));
   if (const char* e = getenv("B200BO_BAND_MODEL")) h->use_model = atoi(e) != 0;
   if (const char* e = getenv("B200BO_DEV_CHUNK_TILES")) h->dev_chunk_tiles = std::max(0, atoi(e));
@@ -419,6 +520,7 @@ int b200bo_destroy(b200bo_handle h) {
   h->band_count.release(); h->err_flag.release();
   h->Xall.release(); h->f_mse.release(); h->bd_kst.release(); h->bd_ypart.release(); h->bd_part.release();
   h->ap_Tr.release(); h->ap_Ts.release(); h->ap_Tu.release(); h->ap_Cb.release(); h->ap_Dv.release();
+  h->oz_dig.release(); h->oz_scA.release(); h->oz_scB.release();
   h->pm_v.release(); h->pm_t.release(); h->pm_t2.release(); h->rowsq.release(); h->rowl1.release(); h->bd_ctl.release();
   if (h->pin) cudaFreeHost(h->pin);
   for (int i = 0; i < 2; ++i) {
@@ -487,6 +589,65 @@ int b200bo_set_keep_R(b200bo_handle h, int keep) {
   CHECK_ARG(h, "handle is NULL");
   h->keepR = keep != 0;
   return 0;
+}
+
+int b200bo_set_chol_tc(b200bo_handle h, int digits, int min_rows) {
+  CHECK_ARG(h, "handle is NULL");
+  CHECK_ARG(digits == 0 || digits == 7 || digits == 8, "digits must be 0 (fp64 DMMA), 7 or 8");
+  h->chol_tc = digits;
+  if (min_rows > 0) h->chol_tc_min_rows = std::max(64, min_rows);
+  return 0;
+}
+
+int b200bo_debug_oz_syrk(b200bo_handle h, const double* P_host, int rows, double* C_host, int digits, int reps, double* out_ms) {
+  CHECK_ARG(h && P_host && C_host, "NULL argument");
+  CHECK_ARG(rows > 0 && rows % 64 == 0, "rows must be a positive multiple of 64");
+  CHECK_ARG(digits == 7 || digits == 8 || digits == 0, "digits must be 7 or 8 (0: the fp64 DMMA kernel, for comparison)");
+  CU_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  DevBuf<double> P, Cd;
+  CU_TRY(P.reserve((size_t)rows * 64));
+  CU_TRY(Cd.reserve((size_t)rows * rows));
+  CU_TRY(cudaMemcpyAsync(P.p, P_host, (size_t)rows * 64 * 8, cudaMemcpyHostToDevice, st));
+  const int keep = h->chol_tc;
+  h->chol_tc = digits;
+  cudaEvent_t e0, e1;
+  CU_TRY(cudaEventCreate(&e0));
+  CU_TRY(cudaEventCreate(&e1));
+  float best = 0;
+  int rc = 0;
+  for (int r = 0; r < std::max(reps, 1) && !rc; ++r) {
+    CU_TRY(cudaMemcpyAsync(Cd.p, C_host, (size_t)rows * rows * 8, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaEventRecord(e0, st));
+    int launches = 0;
+    if (digits) {
+      rc = launch_oz_syrk(h, st, P.p, 64, rows, Cd.p, rows, launches);
+    } else {
+      GemmArgs g{};
+      g.A = P.p; g.B = P.p; g.C = Cd.p; g.lda = 64; g.ldb = 64; g.ldc = rows; g.K = 64; g.alpha = -1.0; g.beta = 1.0; g.lower_only = 1;
+      cudaError_t e = launch_gemm<GemmNT, false, false>(h, g, rows, rows, 1);
+      if (e != cudaSuccess) rc = set_err(B200BO_E_CUDA, cudaGetErrorString(e));
+    }
+    CU_TRY(cudaEventRecord(e1, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (r == 0 || ms < best) best = ms;
+  }
+  h->chol_tc = keep;
+  if (!rc) {
+    CU_TRY(cudaMemcpyAsync(C_host, Cd.p, (size_t)rows * rows * 8, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    int flag = 0;
+    if (digits && h->err_flag.p) CU_TRY(cudaMemcpy(&flag, h->err_flag.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (flag) rc = set_err(B200BO_E_CUDA, "oz_syrk pipeline wait timed out (code " + std::to_string(flag) + ")");
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  P.release();
+  Cd.release();
+  if (out_ms) *out_ms = best;
+  return rc;
 }
 
 int b200bo_set_train(b200bo_handle h, const double* X, const double* y, int N, int D) {
@@ -634,7 +795,7 @@ static int factor_impl(b200bo_handle h, int corr, const double* theta, int n_the
     }
   }
   const void* const gkey[8] = {h->A.p, h->W.p, h->S.p, h->Dinv.p, h->status.p, (const void*)(intptr_t)ld,
-                               (const void*)(intptr_t)(la ? (h->lookahead >= 2 && ld <= 2048 ? 2 : 1) : 0), (const void*)st};
+                               (const void*)(intptr_t)((la ? (h->lookahead >= 2 && ld <= 2048 ? 2 : 1) : 0) + 16 * h->chol_tc + 1024 * h->chol_tc_min_rows), (const void*)st};
   auto chol_body = [&](int& launches) -> int {
   int last_b = -1;  // index of the last panel whose (b) part went to the helper stream
   if (la && h->lookahead >= 2 && ld <= 2048) {
@@ -657,10 +818,15 @@ static int factor_impl(b200bo_handle h, int corr, const double* theta, int n_the
         GemmArgs bq{};
         bq.A = P1; bq.B = P1; bq.C = h->A.p + (size_t)(jb + 2) * NB * (ld + 1);
         bq.lda = ld; bq.ldb = ld; bq.ldc = ld; bq.K = NB; bq.alpha = -1.0; bq.beta = 1.0; bq.lower_only = 1;
-        CU_TRY((launch_gemm_on<GemmNT, false, false>(h, h->la_stream, bq, (nrows - 1) * NB, (nrows - 1) * NB, 1)));
+        if (h->chol_tc && (nrows - 1) * NB >= h->chol_tc_min_rows) {
+          int rc = launch_oz_syrk(h, h->la_stream, P1, ld, (nrows - 1) * NB, bq.C, ld, launches);
+          if (rc) return rc;
+        } else {
+          CU_TRY((launch_gemm_on<GemmNT, false, false>(h, h->la_stream, bq, (nrows - 1) * NB, (nrows - 1) * NB, 1)));
+          ++launches;
+        }
         CU_TRY(cudaEventRecord(h->la_ev[2 * jb + 1], h->la_stream));
         last_b = jb;
-        ++launches;
       }
     }
   } else
@@ -696,8 +862,14 @@ static int factor_impl(b200bo_handle h, int corr, const double* theta, int n_the
       s.A = P; s.B = P; s.C = h->A.p + (size_t)(jb + 1) * NB * (ld + 1);
       s.lda = ld; s.ldb = ld; s.ldc = ld; s.K = NB; s.alpha = -1.0; s.beta = 1.0; s.lower_only = 1;
       if (!la) {
-        CU_TRY((launch_gemm<GemmNT, false, false>(h, s, mrem, mrem, 1)));
-        launches += 2;
+        if (h->chol_tc && mrem >= h->chol_tc_min_rows) {
+          int rc = launch_oz_syrk(h, st, P, ld, mrem, s.C, ld, launches);
+          if (rc) return rc;
+          ++launches;
+        } else {
+          CU_TRY((launch_gemm<GemmNT, false, false>(h, s, mrem, mrem, 1)));
+          launches += 2;
+        }
         continue;
       }
       if (last_b >= 0) CU_TRY(cudaStreamWaitEvent(st, h->la_ev[2 * last_b + 1], 0));
@@ -708,10 +880,15 @@ static int factor_impl(b200bo_handle h, int corr, const double* theta, int n_the
         CU_TRY(cudaStreamWaitEvent(h->la_stream, h->la_ev[2 * jb], 0));
         GemmArgs b = s;  // (b): columns jb + 2 .. of the trailing matrix, from the rows of P below the first block
         b.A = P + (size_t)NB * ld; b.B = b.A; b.C = s.C + (size_t)NB * (ld + 1);
-        CU_TRY((launch_gemm_on<GemmNT, false, false>(h, h->la_stream, b, mrem - NB, mrem - NB, 1)));
+        if (h->chol_tc && mrem - NB >= h->chol_tc_min_rows) {  // exact int8 digit products on tcgen05 (oz_kernels.cuh)
+          int rc = launch_oz_syrk(h, h->la_stream, b.A, ld, mrem - NB, b.C, ld, launches);
+          if (rc) return rc;
+        } else {
+          CU_TRY((launch_gemm_on<GemmNT, false, false>(h, h->la_stream, b, mrem - NB, mrem - NB, 1)));
+          ++launches;
+        }
         CU_TRY(cudaEventRecord(h->la_ev[2 * jb + 1], h->la_stream));
         last_b = jb;
-        ++launches;
       }
     }
   }
@@ -935,7 +1112,7 @@ static int append_front(b200bo_handle h, int N0, int m, int corr, int mode, doub
   a.alpha = mode == B200BO_MODE_NOISE_ESTIM ? par_last : 1.0;
   const size_t smem = ((size_t)NB * D + D + 1) * sizeof(double);
   if (smem > 48 * 1024) CU_TRY(cudaFuncSetAttribute(kmat_append_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kmat_append_rows_kernel<<<(ld + 255) / 256, 256, smem, st>>>(a);
+  kmat_append_rows_kernel<<<(std::max(ld, N0 + NB) + 255) / 256, 256, smem, st>>>(a);
   CU_TRY(cudaGetLastError());
   append_sym_kernel<<<(NB * NB + 255) / 256, 256, 0, st>>>(h->ap_Cb.p, m);
   CU_TRY(cudaGetLastError());
@@ -1409,33 +1586,14 @@ static int run_candidates_fp64(b200bo_handle h, const double* Xc, int64_t M, int
 // ------------------------------------------------------------------------------------------------------
 // tensor-core path (B200BO_PREC_FAST)
 // ------------------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
 static int make_f16_map(CUtensorMap* map, const __half* base, int inner, int rows, int box_inner, int box_rows);
 static int make_linv_map(CUtensorMap* map, const __half* base, int ld) {
   return make_f16_map(map, base, ld, ld, fk::KC, fk::BN);
 }
 // 2-D fp16 row-major tensor (rows x inner), 128-byte-swizzled boxes of box_rows x box_inner
 static int make_f16_map(CUtensorMap* map, const __half* base, int inner, int rows, int box_inner, int box_rows) {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* f = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    CU_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres));
-    if (!f || qres != cudaDriverEntryPointSuccess) return set_err(B200BO_E_CUDA, "cuTensorMapEncodeTiled is not available");
-    fn = (EncodeTiledFn)f;
-  }
-  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)rows};  // innermost first (for L^-1: k, then the row n)
-  cuuint64_t strides[1] = {(cuuint64_t)inner * sizeof(__half)};
-  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)base, dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return set_err(B200BO_E_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
-  return 0;
+  return make_map_2d(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, base, (uint64_t)inner, (uint64_t)rows, (uint64_t)inner * sizeof(__half),
+                     box_inner, box_rows, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
 static void build_fast_model(b200bo_ctx* h, const std::vector<double>& rowsq, const std::vector<double>& rowl1,

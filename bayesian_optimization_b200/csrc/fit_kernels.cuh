@@ -131,8 +131,8 @@ __global__ void __launch_bounds__(256) kmat_append_rows_kernel(AppendRowsArgs p)
   for (int d = tid; d < p.D; d += 256) th[d] = p.theta[d];
   const double pw = corr_has_extra_param(p.corr) ? p.theta[p.D] : 0.0;
   __syncthreads();
-  const int j = blockIdx.x * 256 + tid;  // column of R
-  if (j >= p.ld) return;
+  const int j = blockIdx.x * 256 + tid;  // column of R; the (64, 64) block Cb spans columns N0 .. N0 + 63, which may
+  if (j >= max(p.ld, p.N0 + NB)) return;  // reach past the pitch (its identity padding must still be written)
   const double s2t = p.sigma2 + p.noise_var;
   const double diag = p.mode == 1 ? (p.sigma2 + p.noise_var) / s2t : (p.mode == 2 ? p.alpha + (1.0 - p.alpha) : 1.0);
   for (int i = 0; i < NB; ++i) {
@@ -148,8 +148,7 @@ __global__ void __launch_bounds__(256) kmat_append_rows_kernel(AppendRowsArgs p)
         v = p.mode == 1 ? (p.sigma2 * r) / s2t : (p.mode == 2 ? p.alpha * r : r);
       }
     }
-    if (j < p.N0) p.Tr[(size_t)i * p.ld + j] = v;
-    else p.Tr[(size_t)i * p.ld + j] = 0.0;
+    if (j < p.ld) p.Tr[(size_t)i * p.ld + j] = j < p.N0 ? v : 0.0;
     const int c = j - p.N0;
     if (c >= 0 && c < NB) p.Cb[i * NB + c] = (i < p.m && c < p.m) ? (c <= i ? v : 0.0) : (i == c ? 1.0 : 0.0);
   }

@@ -118,6 +118,15 @@ int b200bo_set_replay(b200bo_handle h, int budget_mb, int max_chunks);
  * 3 (split fp16, ~1e-6).  b200bo_predict always uses 3. */
 int b200bo_set_fast_products(b200bo_handle h, int products);
 
+/* Cholesky trailing updates (the rank-64 SYRK of scipy.linalg.cholesky's blocked form, gpr.py:795) on the tcgen05
+ * tensor cores: digits = 7 or 8 signed 8-bit digit planes of an exact (error-free) splitting of the float64 panel,
+ * multiplied as int8 x int8 -> int32 (kind::i8) and re-assembled in integer arithmetic (7: float64-grade, 8: sub-ulp);
+ * digits = 0 (default) keeps the fp64 DMMA kernel.  Trailing matrices below min_rows rows stay on DMMA (<= 0: keep). */
+int b200bo_set_chol_tc(b200bo_handle h, int digits, int min_rows);
+/* developer / test hook: C (rows x rows, row-major, in/out) -= P P^T on the lower tiles, P (rows x 64) host arrays;
+ * digits as above (0 = the DMMA kernel); out_ms = best device time of `reps` runs (CUDA events). */
+int b200bo_debug_oz_syrk(b200bo_handle h, const double* P_host, int rows, double* C_host, int digits, int reps, double* out_ms);
+
 /* -- training data: GaussianProcess._check_data (gpr.py:279-310) --------------------------------------
  * X (N,D), y (N,) float64 host pointers.  The pairwise-distance pre-pass l1_cross_distances(X)
  * (gpr.py:48-61) is never materialised: distances are recomputed inside the assembly kernel. */
@@ -243,6 +252,8 @@ int b200bo_debug_fast_check(b200bo_handle h, int64_t stride, int64_t max_samples
  *   B200BO_FAST_PRODUCTS=1|3     fp16 products per MAC of the first acquisition pass (default 1)
  *   B200BO_REPLAY_MB=n           scratch budget of generation 4 (default 64)
  *   B200BO_CHOL_LOOKAHEAD=0|1|2  Cholesky: single stream | look-ahead, separate kernels | fused panel step where faster
+ *   B200BO_CHOL_TC=0|7|8         Cholesky trailing updates on tcgen05 int8 digit planes (= b200bo_set_chol_tc)
+ *   B200BO_CHOL_TC_MIN_ROWS=n    smallest trailing matrix that takes the tensor-core update (default 1024)
  *   B200BO_GRAPHS=0|1            CUDA-graph replay of the factorisation stretches for N <= 2048 (default 1)
  *   B200BO_WAIT_HINT_NS=n        suspend-time hint of the mbarrier waits in the fused kernels
  *   B200BO_BAND_MODEL=0|1        0: band half-widths from the calibration sample only (round-1 behaviour)
