@@ -408,13 +408,16 @@ static int launch_oz_syrk(b200bo_ctx* h, cudaStream_t st, const double* P, int l
     h->oz_map_base = h->oz_dig.p;
     h->oz_map_rcap = Rcap;
   }
+  CUtensorMap mapC;
+  if ((rc = make_map_2d(&mapC, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, C, (uint64_t)rows, (uint64_t)rows, (uint64_t)ldc * 8, oz::TM, oz::TN,
+                        CU_TENSOR_MAP_SWIZZLE_NONE))) return rc;
   if (!h->oz_attr) {
     CU_TRY(cudaFuncSetAttribute(oz::oz_syrk_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(oz::oz_syrk_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::SMEM_BYTES));
     h->oz_attr = true;
   }
   oz::OzArgs a;
-  a.scA = h->oz_scA.p; a.scB = h->oz_scB.p; a.C = C; a.ldc = ldc; a.rows = rows; a.Rcap = Rcap; a.err = h->err_flag.p;
+  a.scA = h->oz_scA.p; a.scB = h->oz_scB.p; a.rows = rows; a.Rcap = Rcap; a.err = h->err_flag.p;
   a.dbg = getenv("B200BO_OZ_DEBUG") ? atoi(getenv("B200BO_OZ_DEBUG")) : 0;
   const int ncb = (rows + oz::TM - 1) / oz::TM, nrb = rows / oz::TN;
   long long tiles = 0;
@@ -427,11 +430,11 @@ static int launch_oz_syrk(b200bo_ctx* h, cudaStream_t st, const double* P, int l
   if (S == 7) {
     oz::oz_split_kernel<7><<<rows_pad / 8, 256, 0, st>>>(P, ldp, rows, rows_pad, Rcap, h->oz_dig.p, h->oz_scA.p, h->oz_scB.p);
     CU_TRY(cudaGetLastError());
-    oz::oz_syrk_kernel<7><<<grid, oz::NT_OZ, oz::SMEM_BYTES, st>>>(h->oz_mapA, h->oz_mapB, a);
+    oz::oz_syrk_kernel<7><<<grid, oz::NT_OZ, oz::SMEM_BYTES, st>>>(h->oz_mapA, h->oz_mapB, mapC, a);
   } else {
     oz::oz_split_kernel<8><<<rows_pad / 8, 256, 0, st>>>(P, ldp, rows, rows_pad, Rcap, h->oz_dig.p, h->oz_scA.p, h->oz_scB.p);
     CU_TRY(cudaGetLastError());
-    oz::oz_syrk_kernel<8><<<grid, oz::NT_OZ, oz::SMEM_BYTES, st>>>(h->oz_mapA, h->oz_mapB, a);
+    oz::oz_syrk_kernel<8><<<grid, oz::NT_OZ, oz::SMEM_BYTES, st>>>(h->oz_mapA, h->oz_mapB, mapC, a);
   }
   CU_TRY(cudaGetLastError());
   launches += 2;
