@@ -228,7 +228,8 @@ struct b200bo_ctx {
   double last_noise_arg = 0, last_beta_fixed = NAN;
   DevBuf<double> ap_Tr, ap_Ts, ap_Tu, ap_Cb, ap_Dv;
   int last_q = 0;                 // criteria of the last acquisition call (b200bo_best_pairs_device)
-  int dev_chunk_tiles = 0;        // B200BO_DEV_CHUNK_TILES: fused launches of this many tiles per SM on device-resident input
+  int dev_chunk_tiles = 8;        // B200BO_DEV_CHUNK_TILES: fused launches of this many tiles per SM on device-resident input
+                                  // (0 = one launch; 8 measured 4 % faster at M = 1e7 under the power cap, profiles/r02/device_path_chunking_ab.txt)
   std::vector<double> Xhost;      // training set as given (N, D): the distance-error bound needs max_j ||x_j||^2 per theta
   DevBuf<double> Xall, f_mse, bd_kst, bd_ypart, bd_part, pm_v, pm_t, pm_t2, rowsq, rowl1;
   DevBuf<bd::BandCtl> bd_ctl;

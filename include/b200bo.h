@@ -74,9 +74,13 @@ typedef struct b200bo_ctx* b200bo_handle;
 
 /* precision of the M-candidate predict path */
 #define B200BO_PREC_FP64 0 /* fp64 DMMA, parity path (default)                                          */
-#define B200BO_PREC_FAST 1 /* split-fp16 tcgen05 tensor-core pass (~1e-6) + fp64 re-score of the arg-max band:
-                              b200bo_acq returns the exact fp64 best_val / best_idx; b200bo_predict returns the
-                              approximate moments.  Calls that ask for all q x M values run on the fp64 path. */
+#define B200BO_PREC_FAST 1 /* tcgen05 tensor-core pass + fp64 re-score of the arg-max band: b200bo_acq returns the
+                              exact fp64 best_val / best_idx; b200bo_predict returns approximate moments (three
+                              split-fp16 products per MAC on an fp32 cross-correlation).  Their stated tolerance is
+                              per fit: |d yhat| <= dy_model, |d mse| <= ds_abs_3 + ds_rel_3 sqrt(sum rt^2) of
+                              b200bo_get_band_info; measured <= 3.2e-4 and <= 5e-5 sigma2 (1.5e-4 for Matern-1/2) on
+                              the test shapes and bench workloads (profiles/r02/fast_predict_errors_*.json, enforced by
+                              tests/test_fast_gpu.py).  Calls that ask for all q x M values run on the fp64 path. */
 
 /* state ids for b200bo_get_state */
 #define B200BO_STATE_L 0     /* Cholesky factor "C"   (N,N) lower, zeros above   gpr.py:408, :795 */
@@ -115,7 +119,7 @@ int b200bo_set_fast_kernel(b200bo_handle h, int generation);
 int b200bo_set_replay(b200bo_handle h, int budget_mb, int max_chunks);
 /* fp16 products per MAC of the first tensor-core pass of b200bo_acq: 1 (default; operands rounded to fp16, ~1e-3 on
  * the variance -- the band it leaves is re-scored in fp64, or the call escalates to 3 when the band is too wide) or
- * 3 (split fp16, ~1e-6).  b200bo_predict always uses 3. */
+ * 3 (split fp16: ~2^-22 per product; the fp32 cross-correlation then dominates the error).  b200bo_predict always uses 3. */
 int b200bo_set_fast_products(b200bo_handle h, int products);
 
 /* Cholesky trailing updates (the rank-64 SYRK of scipy.linalg.cholesky's blocked form, gpr.py:795) on the tcgen05
@@ -257,7 +261,7 @@ int b200bo_debug_fast_check(b200bo_handle h, int64_t stride, int64_t max_samples
  *   B200BO_GRAPHS=0|1            CUDA-graph replay of the factorisation stretches for N <= 2048 (default 1)
  *   B200BO_WAIT_HINT_NS=n        suspend-time hint of the mbarrier waits in the fused kernels
  *   B200BO_BAND_MODEL=0|1        0: band half-widths from the calibration sample only (round-1 behaviour)
- *   B200BO_DEV_CHUNK_TILES=n     device-resident input: fused launches of n candidate tiles per SM (0 = one launch)
+ *   B200BO_DEV_CHUNK_TILES=n     device-resident input: fused launches of n candidate tiles per SM (default 8; 0 = one launch)
  *   B200BO_TRACE=path            dump a clock64 timeline of CTA 0 of the fused kernel (Matern-5/2, one product) */
 
 /* -- instrumentation ------------------------------------------------------------------------------------
