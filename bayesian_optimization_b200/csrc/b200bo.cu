@@ -21,6 +21,7 @@
 #include "fast3_kernels.cuh"
 #include "fast4_kernels.cuh"
 #include "fast5_kernels.cuh"
+#include "fast6_kernels.cuh"
 #include "fit_kernels.cuh"
 #include "grad_kernels.cuh"
 #include "host_qr.h"
@@ -197,8 +198,12 @@ struct b200bo_ctx {
   DevBuf<__half> r_scratch;
   int replay_mb = 64;           // scratch budget (MB): sized to stay in L2 next to the fp16 L^-1; 0 = recompute (generation 3)
   std::vector<double> xmean;  // per-feature mean of the training set (host copy from set_train)
-  int fast_kernel_pref = 5;   // 5: CTA pairs, producers decoupled through the scratch; 4: CTA pairs + r replay; 3: CTA pairs; 2: single-CTA Gram kernel; 1: first generation
+  int fast_kernel_pref = 6;   // 6: two CTA pairs share a candidate tile (L2-resident scratch); 5: CTA pairs, producers decoupled through the scratch; 4: CTA pairs + r replay; 3: CTA pairs; 2: single-CTA Gram kernel; 1: first generation
   bool use_decoupled = false;
+  bool use_shared = false;    // generation 6 applies to this fit (ld % 256 == 0, ld >= 1024, all CTAs co-resident)
+  int shared_ok = -1;         // occupancy query of generation 6: -1 not asked yet, 0 no, 1 yes
+  DevBuf<uint32_t> share_flags;
+  int last_gen = 0;           // generation of the fused kernel the last tensor-core launch used (timings[10])
   cudaStream_t copy_stream = nullptr;
   cudaStream_t la_stream = nullptr;  // low-priority helper stream of the Cholesky look-ahead
   cudaStream_t inv_stream = nullptr; // diagonal-block inverses, off the critical path
@@ -489,7 +494,7 @@ int b200bo_create(int device, b200bo_handle* out) {
   CU_TRY(h->status.reserve(1));
   // developer knobs (A/B runs): first-pass products and the mbarrier suspend hint of the fused kernels
   if (const char* e = getenv("B200BO_FAST_PRODUCTS")) h->fast_products = atoi(e) == 3 ? 3 : 1;
-  if (const char* e = getenv("B200BO_FAST_KERNEL")) h->fast_kernel_pref = std::max(1, std::min(5, atoi(e)));
+  if (const char* e = getenv("B200BO_FAST_KERNEL")) h->fast_kernel_pref = std::max(1, std::min(6, atoi(e)));
   if (const char* e = getenv("B200BO_CHOL_LOOKAHEAD")) h->lookahead = std::max(0, std::min(2, atoi(e)));
   if (const char* e = getenv("B200BO_GRAPHS")) h->use_graphs = atoi(e) != 0;
   if (const char* e = getenv("B200BO_CHOL_TC")) { int v = atoi(e); h->chol_tc = (v == 7 || v == 8) ? v : 0; }
@@ -524,7 +529,7 @@ int b200bo_destroy(b200bo_handle h) {
   h->band_count.release(); h->err_flag.release();
   h->Xall.release(); h->f_mse.release(); h->bd_kst.release(); h->bd_ypart.release(); h->bd_part.release();
   h->ap_Tr.release(); h->ap_Ts.release(); h->ap_Tu.release(); h->ap_Cb.release(); h->ap_Dv.release();
-  h->oz_dig.release(); h->oz_scA.release(); h->oz_scB.release();
+  h->oz_dig.release(); h->oz_scA.release(); h->oz_scB.release(); h->share_flags.release();
   h->pm_v.release(); h->pm_t.release(); h->pm_t2.release(); h->rowsq.release(); h->rowl1.release(); h->bd_ctl.release();
   if (h->pin) cudaFreeHost(h->pin);
   for (int i = 0; i < 2; ++i) {
@@ -562,7 +567,7 @@ int b200bo_set_precision(b200bo_handle h, int prec) {
 
 int b200bo_set_fast_kernel(b200bo_handle h, int generation) {
   CHECK_ARG(h, "handle is NULL");
-  CHECK_ARG(generation >= 1 && generation <= 5, "generation is 1 .. 5");
+  CHECK_ARG(generation >= 1 && generation <= 6, "generation is 1 .. 6");
   h->fast_kernel_pref = generation;
   h->fast_ready = false;
   h->fvec_ready = false;
@@ -1688,6 +1693,25 @@ static int ensure_fast_state(b200bo_handle h) {
       h->use_decoupled = h->fast_kernel_pref >= 5 && ld >= 512 && want * sizeof(__half) <= ((size_t)4 << 30);
       const size_t n_halves = h->use_decoupled ? want : std::min(want, cap);
       h->use_replay = h->fast_kernel_pref >= 4 && n_halves >= (size_t)h->num_sms * 2 * blk;
+      h->use_shared = false;
+      if (h->fast_kernel_pref >= 6 && h->use_decoupled && ld % 256 == 0 && ld >= 1024 && h->num_sms % 4 == 0) {
+        if (h->shared_ok < 0) {
+          // the partner pairs of generation 6 poll each other: every CTA of the grid has to be resident at once
+          cudaLaunchConfig_t cfg = {};
+          cfg.gridDim = dim3(h->num_sms); cfg.blockDim = dim3(fk6::NT6); cfg.dynamicSmemBytes = fk6::SMEM6_BYTES;
+          cudaLaunchAttribute at[1];
+          at[0].id = cudaLaunchAttributeClusterDimension;
+          at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+          cfg.attrs = at; cfg.numAttrs = 1;
+          auto kern = fk6::predict_fused_shared_kernel<MATERN52, 1>;
+          CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fk6::SMEM6_BYTES));
+          int ncl = 0;
+          cudaError_t e = cudaOccupancyMaxActiveClusters(&ncl, kern, &cfg);
+          h->shared_ok = (e == cudaSuccess && ncl * 2 >= h->num_sms) ? 1 : 0;
+          if (e != cudaSuccess) cudaGetLastError();
+        }
+        h->use_shared = h->shared_ok == 1;
+      }
       if (h->use_replay) {
         CU_TRY(h->r_scratch.reserve(n_halves));
         h->replay_maps.pm = h->pair_maps;
@@ -1798,7 +1822,52 @@ static int launch_fused(b200bo_handle h, const double* xc_dev, long long m, size
     CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fk2::SMEM_BYTES));              \
     kern<<<grid, fk2::NT2, fk2::SMEM_BYTES, h->stream>>>(h->map2_hi, h->map2_lo, h->map2_xh, h->map2_xl, a);        \
   } while (0)
-    if (h->use_pair && h->use_replay && h->use_decoupled) {
+    if (h->use_pair && h->use_replay && h->use_decoupled && h->use_shared) {
+      h->last_gen = 6;
+      fk4::ReplayArgs ra;
+      ra.scratch = h->r_scratch.p;
+      ra.n_store = h->ld / fk::KC;
+      h->last_n_store = ra.n_store;
+      // deal the accumulator super-tiles to the two sides of a group: largest first, to the side that carries less
+      const int n_super = (h->ld + fk2::WC - 1) / fk2::WC;
+      uint32_t mask = 0;
+      long long load[2] = {0, 0};
+      for (int s = n_super - 1; s >= 0; --s) {
+        const int uses = std::min(h->ld, fk2::WC * (s + 1)) / fk::KC;
+        const int side = load[1] < load[0] ? 1 : 0;
+        load[side] += uses;
+        if (side) mask |= 1u << s;
+      }
+      fk6::ShareArgs sa;
+      const long long ptiles = (tiles + 1) / 2;
+      const int groups = (int)std::min<long long>(h->num_sms / 4, ptiles);
+      const int grid6 = 4 * groups;
+      const size_t nflags = (size_t)groups * 2 * 2 * 3 * 8;
+      CU_TRY(h->share_flags.reserve((size_t)(h->num_sms / 4) * 2 * 2 * 3 * 8));
+      CU_TRY(cudaMemsetAsync(h->share_flags.p, 0, nflags * sizeof(uint32_t), h->stream));
+      // the two sides ADD their parts into the outputs
+      const size_t mp = (size_t)tiles * fk::BM;
+      CU_TRY(cudaMemsetAsync(a.yhat, 0, mp * 8, h->stream));
+      CU_TRY(cudaMemsetAsync(a.sumsq, 0, mp * 8, h->stream));
+      CU_TRY(cudaMemsetAsync(a.dotf, 0, mp * 8, h->stream));
+      sa.flags = h->share_flags.p;
+      sa.side_mask = mask;
+      sa.dead_hint = getenv("B200BO_GEN6_DEAD_HINT") ? atoi(getenv("B200BO_GEN6_DEAD_HINT")) : 0;
+#define FK6_LAUNCH(C)                                                                                               \
+  do {                                                                                                             \
+    auto kern = nprod == 1 ? fk6::predict_fused_shared_kernel<C, 1> : fk6::predict_fused_shared_kernel<C, 3>;       \
+    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fk6::SMEM6_BYTES));             \
+    kern<<<grid6, fk6::NT6, fk6::SMEM6_BYTES, h->stream>>>(h->replay_maps, a, ra, sa);                              \
+  } while (0)
+      switch (h->corr) {
+        case RBF: FK6_LAUNCH(RBF); break;
+        case MATERN12: FK6_LAUNCH(MATERN12); break;
+        case MATERN32: FK6_LAUNCH(MATERN32); break;
+        default: FK6_LAUNCH(MATERN52); break;
+      }
+#undef FK6_LAUNCH
+    } else if (h->use_pair && h->use_replay && h->use_decoupled) {
+      h->last_gen = 5;
       fk4::ReplayArgs ra;
       ra.scratch = h->r_scratch.p;
       ra.n_store = h->ld / fk::KC;
@@ -1810,6 +1879,7 @@ static int launch_fused(b200bo_handle h, const double* xc_dev, long long m, size
         default: FK5_LAUNCH(MATERN52); break;
       }
     } else if (h->use_pair && h->use_replay) {
+      h->last_gen = 4;
       fk4::ReplayArgs ra;
       ra.scratch = h->r_scratch.p;
       const size_t blk = (size_t)fk::BM * fk::KC;
@@ -1824,6 +1894,7 @@ static int launch_fused(b200bo_handle h, const double* xc_dev, long long m, size
         default: FK4_LAUNCH(MATERN52); break;
       }
     } else if (h->use_pair) {
+      h->last_gen = 3;
       switch (h->corr) {
         case RBF: FK3_LAUNCH(RBF); break;
         case MATERN12: FK3_LAUNCH(MATERN12); break;
@@ -1831,6 +1902,7 @@ static int launch_fused(b200bo_handle h, const double* xc_dev, long long m, size
         default: FK3_LAUNCH(MATERN52); break;
       }
     } else {
+      h->last_gen = 2;
       switch (h->corr) {
         case RBF: FK2_LAUNCH(RBF); break;
         case MATERN12: FK2_LAUNCH(MATERN12); break;
@@ -1861,6 +1933,7 @@ static int launch_fused(b200bo_handle h, const double* xc_dev, long long m, size
     }
     return 0;
   }
+  h->last_gen = 1;
   fk::FusedArgs a;
   a.Xc = xc_dev; a.Xs = h->Xs.p; a.cscale = h->cscale.p;
   a.yhat = h->f_yhat.p + out_off; a.sumsq = h->f_sumsq.p + out_off; a.dotf = h->f_dotf.p + out_off;
@@ -2089,6 +2162,7 @@ static int run_candidates_fast(b200bo_handle h, const double* Xc, int64_t M, int
     h->timings[0] = ms; h->timings[1] = 0; h->timings[2] = pt.total(1); h->timings[3] = 0;
     h->timings[4] = fused_launches; h->timings[5] = lc.all; h->timings[6] = 0; h->timings[7] = 0;
     h->timings[8] = 3;
+    h->timings[10] = h->last_gen;
     return 0;
   }
 
@@ -2256,6 +2330,7 @@ static int run_candidates_fast(b200bo_handle h, const double* Xc, int64_t M, int
   h->timings[0] = ms; h->timings[1] = 0; h->timings[2] = pt.total(1); h->timings[3] = ms - pt.total(1);
   h->timings[4] = fused_launches; h->timings[5] = lc.all; h->timings[6] = rescored; h->timings[7] = passes;
   h->timings[8] = nprod; h->timings[9] = (nprod == 3 && h->escalate) ? 1 : 0;
+  h->timings[10] = h->last_gen;
   return 0;
 }
 

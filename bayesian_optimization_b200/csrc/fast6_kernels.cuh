@@ -16,7 +16,12 @@
 //     monotonic counters in global memory (writer: st.global, fence.proxy.async, CTA barrier, st.release.gpu of the
 //     counter; reader: ld.acquire.gpu, fence.proxy.async, cp.async.bulk.tensor), chunks of the own side through the
 //     shared-memory counters of generation 5.  A slot is rewritten for the next tile once BOTH sides have retired
-//     their last replay of it (own consumed-use counter in shared memory, the partner's in global memory).
+//     their last replay of it (own consumed-use counter in shared memory, the partner's in global memory);
+//   * none of the working warps touches the global counters: a 25th "mailbox" warp publishes this side's three
+//     shared-memory counters (st.release.gpu) and mirrors the partner's into shared memory (ld.acquire.gpu ->
+//     st.release.cta).  The first version had the producers' elected thread fence + release to global memory and poll
+//     the partner's counter once per chunk, inside the 256-thread barrier of its group: the tensor pipe fell to 41 %
+//     (profiles/r02/gen6_first_*).  The hand-over latency (~3 us) is covered by the producers' head start.
 //
 // The partner pairs poll each other, so all CTAs of the grid must be co-resident: the host launches at most one CTA
 // per SM and falls back to generation 5 when the occupancy query does not confirm it.  Everything else (cta_group::2
@@ -31,10 +36,20 @@ namespace fk6 {
 
 using namespace fk3;
 using namespace fk5;
+// the barrier map is generation 5's (fk3 declares an older one under the same names)
+using fk5::BAR_FULL; using fk5::BAR_EMPTY_ST; using fk5::BAR_FULL_X; using fk5::BAR_EMPTY_X; using fk5::BAR_FULL_G;
+using fk5::BAR_EMPTY_G; using fk5::BAR_FULL_AX; using fk5::BAR_ACC_FULL; using fk5::BAR_ACC_EMPTY; using fk5::BAR_FULL_AUX;
+using fk5::BAR_EMPTY_AUX; using fk5::SLOT_TMEM; using fk5::SLOT_PROD; using fk5::SLOT_CONS;
+
+constexpr int NT6 = NT2 + 32;               // + the mailbox warp
+constexpr int MIRROR_OFF = 320;             // byte offset of the mirror words behind the barrier block
+constexpr int SMEM6_BYTES = fk3::SMEM_BYTES + 64;
+static_assert(SMEM6_BYTES <= 232448, "shared memory budget");
 
 struct ShareArgs {
   uint32_t* flags;     // (groups, 2 ranks, 2 sides, 3 counters) x 8 words (one 32-byte sector per counter), zeroed per launch
   uint32_t side_mask;  // bit s = side that owns accumulator super-tile s
+  int dead_hint;       // 1: the last replay of a chunk is loaded with L2::evict_first (generation 5's habit)
 };
 
 __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
@@ -44,6 +59,11 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
 }
 __device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_global_256(void* p, const uint32_t (&v)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+               "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
 }
 // wait until the monotonic global counter reaches `need`; `seen` caches the last value read (the counters only grow, so
 // a cached value that already suffices saves the ~700-cycle round trip to L2)
@@ -88,7 +108,7 @@ __device__ __forceinline__ uint32_t dead_after(const SidePlan& sp, uint32_t tl, 
 }
 
 template <int CORR, int NPROD>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT2, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT6, 1)
 predict_fused_shared_kernel(const __grid_constant__ fk4::ReplayMaps rmaps, const Fused2Args p, const fk4::ReplayArgs ra,
                             const ShareArgs sh) {
   const PairMaps& maps = rmaps.pm;
@@ -100,6 +120,7 @@ predict_fused_shared_kernel(const __grid_constant__ fk4::ReplayMaps rmaps, const
   uint32_t* tmem_slot = (uint32_t*)(bars + SLOT_TMEM);
   const uint32_t prod_cnt = BAR(SLOT_PROD), cons_cnt = BAR(SLOT_CONS);
   constexpr int ST = NPROD == 1 ? 4 : 2;
+  const uint32_t mir = bar0 + (uint32_t)MIRROR_OFF;   // partner's counters, mirrored by the mailbox warp: prod 0, prod 1, consumed
   constexpr int PLANES = NPROD == 1 ? 1 : 2;
   constexpr int A_STRIDE = NPROD == 1 ? A_HALF_BYTES : A_STAGE_BYTES;
   constexpr int B_STRIDE = NPROD == 1 ? BA_PLANE + BB_PLANE : 2 * (BA_PLANE + BB_PLANE);
@@ -161,6 +182,7 @@ predict_fused_shared_kernel(const __grid_constant__ fk4::ReplayMaps rmaps, const
     ((volatile uint32_t*)(bars + SLOT_PROD))[0] = 0u;
     ((volatile uint32_t*)(bars + SLOT_PROD))[1] = 0u;
     ((volatile uint32_t*)(bars + SLOT_CONS))[0] = 0u;
+    for (int i = 0; i < 3; ++i) ((volatile uint32_t*)(smem + OFF_BAR + MIRROR_OFF))[i] = 0u;
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -180,11 +202,10 @@ predict_fused_shared_kernel(const __grid_constant__ fk4::ReplayMaps rmaps, const
       const uint32_t full0 = LBAR(BAR_FULL);
       const uint64_t pol_keep = l2_policy_evict_last(), pol_norm = l2_policy_evict_normal(), pol_dead = l2_policy_evict_first();
       // chunk kc of local tile tl has been stored (by whichever side owns it)
-      uint32_t seen_ot[2] = {0u, 0u};
       auto wait_chunk = [&](int kc, uint32_t tl) {
         const uint32_t need = tl * (uint32_t)(nch / 4) + (uint32_t)(kc >> 2) + 1u;
         if ((uint32_t)((kc >> 1) & 1) == side) spin_until_ge(prod_cnt + 4u * (uint32_t)(kc & 1), need, p.err, 14);
-        else spin_until_ge_gpu(fl_ot + 8 * (kc & 1), need, seen_ot[kc & 1], p.err, 16);
+        else spin_until_ge(mir + 4u * (uint32_t)(kc & 1), need, p.err, 16);
       };
       uint32_t it = 0, tl = 0, st = 0, ph = 0;
       for (long long pt = group; pt < n_ptiles; pt += n_groups, ++tl) {
@@ -209,15 +230,12 @@ predict_fused_shared_kernel(const __grid_constant__ fk4::ReplayMaps rmaps, const
             const int kc = ci < n_bulk ? (desc ? n_bulk - 1 - ci : ci) : ci;
             const int k0 = kc * KC;
             mbar_wait_fast(BAR(BAR_EMPTY_ST + st), ph ^ 1, p.err, 1);
-            if (el && it >= (uint32_t)ST) {
-              st_release_cta(cons_cnt, it - ST + 1);
-              st_release_gpu(fl_me + 16, it - ST + 1);
-            }
+            if (el && it >= (uint32_t)ST) st_release_cta(cons_cnt, it - ST + 1);
             const uint32_t fb = full0 + 8u * st;
             const uint32_t da = sbase + OFF_A + st * A_STRIDE;
             const uint32_t dst = sbase + OFF_B + st * B_STRIDE;
             if (k0 < n0 && act_2) {
-              const uint64_t pol_a = s == n_super - 1 ? pol_dead : pol_norm;
+              const uint64_t pol_a = (s == n_super - 1 && sh.dead_hint) ? pol_dead : pol_norm;
               mbar_expect_tx_cluster_p(fb, a_bytes + (uint32_t)((BA_PLANE + BB_PLANE) * PLANES), el);
               tma_load_2d_pair_hint(da, &rmaps.scr, 0, scr_row(kc, 0), fb, pol_a, el);
               if (NPROD == 3) tma_load_2d_pair_hint(da + A_HALF_BYTES, &rmaps.scr, 0, scr_row(kc, 1), fb, pol_a, el);
@@ -257,14 +275,14 @@ predict_fused_shared_kernel(const __grid_constant__ fk4::ReplayMaps rmaps, const
           }
         }
       }
-      // the last ST uses: publish them once their MMAs have retired (the partner's producers of a LATER tile never wait
-      // for these -- there is no later tile -- but a counter that ends at its final value keeps the protocol checkable)
+      // the last ST uses: publish them once their MMAs have retired (the mailbox warp leaves when the counters have
+      // reached their final values)
       for (int k = 0; k < ST && it > 0; ++k) {
         mbar_wait_fast(BAR(BAR_EMPTY_ST + st), ph ^ 1, p.err, 1);
         st = (st + 1) & (ST - 1);
         ph ^= (st == 0);
       }
-      if (el && it > 0) st_release_gpu(fl_me + 16, it);
+      if (el && it > 0) st_release_cta(cons_cnt, it);
     }
   } else if (warp == 3) {
     // ================================ TMA: training block halves + aux, once per (tile, own chunk) ================
@@ -474,7 +492,7 @@ predict_fused_shared_kernel(const __grid_constant__ fk4::ReplayMaps rmaps, const
       }
       if (tile < n_tiles) atomicAdd(p.sumsq + tile * BM + row, ss);   // two addends (one per side) on a zeroed array
     }
-  } else if (warp >= PW0) {
+  } else if (warp >= PW0 && warp < PW0 + NPW) {
     // ================================ producers (own 128 candidates, this side's chunks) ================================
     const int pw = warp - PW0;
     const int grp = pw >> 3;
@@ -487,7 +505,7 @@ predict_fused_shared_kernel(const __grid_constant__ fk4::ReplayMaps rmaps, const
     const float CG = -2.0f / (float)(1 << (2 * X_SCALE_LOG2));
     const bool elected = (pw & 7) == 0 && lane == 0;
     uint8_t* const scr = (uint8_t*)ra.scratch;
-    uint32_t j = 0, tl = 0, done = 0, seen_cons = 0;
+    uint32_t j = 0, tl = 0, done = 0;
     for (long long pt = group; pt < n_ptiles; pt += n_groups, ++tl) {
       const long long tile = 2 * pt + rank;
       float am;
@@ -537,7 +555,7 @@ predict_fused_shared_kernel(const __grid_constant__ fk4::ReplayMaps rmaps, const
         // the scratch slot of this chunk is free once BOTH sides have retired the previous tile's last replay of it
         if (elected && tl > 0) {
           spin_until_ge(cons_cnt, dead_after(me, tl, kc), p.err, 15);
-          spin_until_ge_gpu(fl_ot + 16, dead_after(ot, tl, kc), seen_cons, p.err, 17);
+          spin_until_ge(mir + 8u, dead_after(ot, tl, kc), p.err, 17);
         }
         if (grp == 0) asm volatile("bar.sync 1, %0;" ::"n"(32 * NPW / 2) : "memory");
         else asm volatile("bar.sync 2, %0;" ::"n"(32 * NPW / 2) : "memory");
@@ -565,24 +583,23 @@ predict_fused_shared_kernel(const __grid_constant__ fk4::ReplayMaps rmaps, const
             ysum = fmaf(kv[i], gj.x, fmaf(kv[i + 1], gj.y, fmaf(kv[i + 2], gj.z, fmaf(kv[i + 3], gj.w, ysum))));
             fsum = fmaf(kv[i], fj.x, fmaf(kv[i + 1], fj.y, fmaf(kv[i + 2], fj.z, fmaf(kv[i + 3], fj.w, fsum))));
           }
+          // 16 fp16 values = one 32-byte sector per plane, written with ONE 256-bit store (two 16-byte stores are two
+          // partial-sector writes for L2: ncu showed a DRAM fill read for every scratch line)
+          uint32_t hi[8], lo[8];
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            uint32_t hi[4], lo[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float v0 = kv[8 * c + 2 * i], v1 = kv[8 * c + 2 * i + 1];
-              const __half2 hh = __floats2half2_rn(v0, v1);
-              hi[i] = *(const uint32_t*)&hh;
-              if (NPROD == 3) {
-                const float2 hf = __half22float2(hh);
-                const __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
-                lo[i] = *(const uint32_t*)&l;
-              }
+          for (int i = 0; i < 8; ++i) {
+            const float v0 = kv[2 * i], v1 = kv[2 * i + 1];
+            const __half2 hh = __floats2half2_rn(v0, v1);
+            hi[i] = *(const uint32_t*)&hh;
+            if (NPROD == 3) {
+              const float2 hf = __half22float2(hh);
+              const __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+              lo[i] = *(const uint32_t*)&l;
             }
-            const uint32_t goff = (uint32_t)(((col0 >> 3) + c) * 16);
-            *(uint4*)(g_hi + goff) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            if (NPROD == 3) *(uint4*)(g_lo + goff) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           }
+          const uint32_t goff = (uint32_t)((col0 >> 3) * 16);  // plain row-major: the TMA load applies the swizzle
+          st_global_256(g_hi + goff, hi);
+          if (NPROD == 3) st_global_256(g_lo + goff, lo);
         }
         ysum_d += (double)ysum;
         fsum_d += (double)fsum;
@@ -591,8 +608,6 @@ predict_fused_shared_kernel(const __grid_constant__ fk4::ReplayMaps rmaps, const
         else asm volatile("bar.sync 2, %0;" ::"n"(32 * NPW / 2) : "memory");
         ++done;
         if (elected) {
-          __threadfence();                                     // the group's stores, cumulatively, before the gpu-scope release
-          st_release_gpu(fl_me + 8 * grp, done);
           st_release_cta(prod_cnt + 4u * (uint32_t)grp, done);
           mbar_arrive(BAR(BAR_EMPTY_AUX + ax));
         }
@@ -613,6 +628,36 @@ predict_fused_shared_kernel(const __grid_constant__ fk4::ReplayMaps rmaps, const
         atomicAdd(p.dotf + tile * BM + m, f);
       }
       asm volatile("bar.sync 3, %0;" ::"n"(32 * NPW) : "memory");
+    }
+  }
+  else if (warp == PW0 + NPW) {
+    // ================================ mailbox: this side's counters -> global, the partner's -> shared memory ==========
+    // acquire.cta on a local counter orders the producers' scratch stores (st.global + fence.proxy.async + their CTA
+    // barrier + st.release.cta) before the release.gpu below; on the other side acquire.gpu + release.cta hand the same
+    // guarantee to the TMA warp, which adds its own fence.proxy.async before the cp.async.bulk.tensor.
+    if (lane == 0) {
+      uint32_t n_my = 0;
+      for (long long pt = group; pt < n_ptiles; pt += n_groups) ++n_my;
+      const uint32_t fin_prod = n_my * (uint32_t)(nch / 4), fin_cons = n_my * (uint32_t)me.upt;
+      uint32_t pub0 = 0, pub1 = 0, pubc = 0;
+      const long long t0 = clock64();
+      while (n_my) {
+        const uint32_t p0 = ld_acquire_cta(prod_cnt), p1 = ld_acquire_cta(prod_cnt + 4u), pc = ld_acquire_cta(cons_cnt);
+        if (p0 != pub0) st_release_gpu(fl_me + 0, pub0 = p0);
+        if (p1 != pub1) st_release_gpu(fl_me + 8, pub1 = p1);
+        if (pc != pubc) st_release_gpu(fl_me + 16, pubc = pc);
+        const uint32_t q0 = ld_acquire_gpu(fl_ot + 0), q1 = ld_acquire_gpu(fl_ot + 8), qc = ld_acquire_gpu(fl_ot + 16);
+        st_release_cta(mir + 0u, q0);
+        st_release_cta(mir + 4u, q1);
+        st_release_cta(mir + 8u, qc);
+        if (pub0 == fin_prod && pub1 == fin_prod && pubc == fin_cons) break;
+        __nanosleep(64);
+        if (clock64() - t0 > 16 * WAIT_TIMEOUT_CYCLES) {
+          atomicExch(p.err, 18);
+          __threadfence_system();
+          __trap();
+        }
+      }
     }
   }
   tc_fence_before();

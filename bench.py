@@ -28,9 +28,14 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "gp_predict_acq_candidates_per_sec"
-# dram__bytes_read.sum + dram__bytes_write.sum PER CANDIDATE of the fused kernel (generation 5) from the ncu --set full
-# capture of a 75776-candidate launch (profiles/r01/gen5_final_ncu_summary.txt): the r scratch (148 MB at C3) does not fit L2
-NCU_TRAFFIC_PER_CAND = {("C3", 1): (2.047070e9 + 649.5e6) / 75776}
+# dram__bytes_read.sum + dram__bytes_write.sum PER CANDIDATE of the fused kernel, from ncu --set full captures of one launch
+# of that workload (profiles/): keyed (workload, products per MAC, kernel generation).  Generation 5 keeps a 148 MB r
+# scratch at C3 (does not fit L2: profiles/r01/gen5_final_ncu_summary.txt, 75776 candidates); generation 6 halves it
+# (profiles/r02/gen6_final_ncu_summary.txt, 151552 candidates).  ncu-derived, not measured in-run.
+NCU_TRAFFIC_PER_CAND = {
+    ("C3", 1, 5): (2.047070e9 + 649.5e6) / 75776,
+    ("C3", 1, 6): (1.667662e9 + 1.230796e9) / 151552,
+}
 UNIT = "candidates/s"
 
 
@@ -189,7 +194,7 @@ def executed_macs(w, nprod):
     absolute_exponential runs generation 1 (512-column super-tiles of two 256-column blocks, no Gram MMA)."""
     ld = -(-w.N // 128) * 128
     gen2 = w.corr != "absolute_exponential"
-    gen5 = gen2 and ld >= 512 and int(os.environ.get("B200BO_FAST_KERNEL", "5")) >= 5
+    gen5 = gen2 and ld >= 512 and int(os.environ.get("B200BO_FAST_KERNEL", "6")) >= 5
     mac = 0
     if gen5:
         for s_ in range(-(-ld // 384)):
@@ -422,11 +427,14 @@ def run_b200(args, w, params):
         exe = cand_per_launch * 2.0 * mac_exec / (launch_ms * 1e-3) / 1e12
         # DRAM traffic of the fused kernel per launch: ncu's per-candidate figure (dram__bytes_read.sum + dram__bytes_write.sum
         # of one --set full capture of this workload, profiles/) x the candidates of one launch
-        tpc = NCU_TRAFFIC_PER_CAND.get((w.name, nprod)) if gen5 else None
+        gen = int(round(kern[10] / args.steps)) if len(kern) > 10 else 0
+        tpc = NCU_TRAFFIC_PER_CAND.get((w.name, nprod, gen))
         roofline["traffic"] = tpc * cand_per_launch if tpc else None
         roofline["traffic_source"] = "ncu --set full capture of this workload (profiles/), bytes per candidate x candidates per launch" if tpc else None
         roofline.update({
-            "kernel": ("predict_fused_decoupled_kernel (tcgen05.mma cta_group::2 kind::f16, M=256, r computed once per tile and replayed by TMA" if gen5
+            "generation": gen,
+            "kernel": ("predict_fused_shared_kernel (tcgen05.mma cta_group::2 kind::f16, M=256, two CTA pairs share a candidate tile: r computed once per group, replayed by TMA from an L2-sized scratch" if gen == 6
+                       else "predict_fused_decoupled_kernel (tcgen05.mma cta_group::2 kind::f16, M=256, r computed once per tile and replayed by TMA" if gen5
                        else "predict_fused_pair_kernel (tcgen05.mma cta_group::2 kind::f16, M=256" if gen2
                        else "predict_fused_tc_kernel (tcgen05.mma kind::f16, M=128") + ", fp32 TMEM accumulators)",
             "executed_tensor_tflops": exe, "executed_frac": exe / peak,

@@ -105,7 +105,9 @@ int b200bo_destroy(b200bo_handle h);
 int b200bo_set_stream(b200bo_handle h, void* cuda_stream);
 int b200bo_set_precision(b200bo_handle h, int prec);
 int b200bo_set_keep_R(b200bo_handle h, int keep);
-/* which tensor-core kernel B200BO_PREC_FAST uses: 5 (default) = CTA pairs, every r chunk computed once per tile into a
+/* which tensor-core kernel B200BO_PREC_FAST uses: 6 (default) = generation 5 with two CTA pairs sharing one candidate
+ * tile: the r chunks are produced once per pair of pairs, the accumulator super-tiles are dealt to the two pairs and the
+ * scratch (half the size) stays in L2 (N % 256 == 0, N >= 1024, all CTAs co-resident; else 5); 5 = CTA pairs, every r chunk computed once per tile into a
  * scratch by producers that run a tile ahead, all A operands by TMA, per-block accumulator drain (N >= 512, else 4);
  * 4 = CTA pairs + replay of r from an L2-resident scratch, first uses written straight into the A ring;
  * 3 = CTA pairs (tcgen05 cta_group::2) sharing the B operands, r recomputed per accumulator super-tile;
@@ -252,7 +254,7 @@ int b200bo_get_band_info(b200bo_handle h, double* out, int n);
 int b200bo_debug_fast_check(b200bo_handle h, int64_t stride, int64_t max_samples, double* out, int n);
 
 /* -- environment knobs read at b200bo_create (developer / A-B switches; the defaults are the measured best) --------
- *   B200BO_FAST_KERNEL=1..5      generation of the fused tensor-core kernel (default 5), = b200bo_set_fast_kernel
+ *   B200BO_FAST_KERNEL=1..6      generation of the fused tensor-core kernel (default 6), = b200bo_set_fast_kernel
  *   B200BO_FAST_PRODUCTS=1|3     fp16 products per MAC of the first acquisition pass (default 1)
  *   B200BO_REPLAY_MB=n           scratch budget of generation 4 (default 64)
  *   B200BO_CHOL_LOOKAHEAD=0|1|2  Cholesky: single stream | look-ahead, separate kernels | fused panel step where faster
@@ -270,7 +272,8 @@ int b200bo_debug_fast_check(b200bo_handle h, int64_t stride, int64_t max_samples
  *   [3] acquisition + arg-max kernels  [4] number of contraction launches  [5] number of all launches
  *   [6] fp64 re-scored candidates (FAST only)  [7] band passes (FAST only)
  * FAST: [1] = 0 (the k* build is fused), [2] = fused tensor-core kernel, [3] = band selection + exact re-score,
- *       [8] fp16 products per MAC of the pass that produced the result (1 or 3)  [9] 1 if this call escalated 1 -> 3 */
+ *       [8] fp16 products per MAC of the pass that produced the result (1 or 3)  [9] 1 if this call escalated 1 -> 3
+ *       [10] generation of the fused kernel that ran (b200bo_set_fast_kernel; the fall-backs for small / odd N apply) */
 #define B200BO_N_TIMINGS 12
 int b200bo_get_timings(b200bo_handle h, double* out, int n);
 /* timings (ms) of the last factor(): [0] total [1] assembly [2] cholesky [3] trtri [4] solves  [5] launches */

@@ -24,6 +24,7 @@ CASES = [  # (N, D, corr name, oracle corr id)
     (300, 3, "matern12", go.CORR_MATERN12),
     (700, 24, "absolute_exponential", go.CORR_ABSEXP),
     (2048, 40, "squared_exponential", go.CORR_RBF),
+    (1024, 6, "matern52", go.CORR_MATERN52),   # generation 6 needs N % 256 == 0, N >= 1024 (as does the case above)
 ]
 
 
@@ -35,13 +36,14 @@ def make(N, D, corr, corr_id, nugget=1e-6):
     return gp, ora
 
 
-@pytest.mark.parametrize("gen", [1, 2, 3, 4, (4, 2), (4, 6), (4, 10), 5])
+@pytest.mark.parametrize("gen", [1, 2, 3, 4, (4, 2), (4, 6), (4, 10), 5, 6])
 @pytest.mark.parametrize("N,D,corr,corr_id", CASES)
 def test_rt_and_moments(N, D, corr, corr_id, gen):
     """gen 1: distances on the CUDA cores; gen 2: Gram product on the tensor cores (L2 kernels only); gen 3: the
     same on CTA pairs (tcgen05 cta_group::2); gen 4: CTA pairs + replay of r from the scratch (everything stored, or
     only the first 2 / 6 / 10 chunks of a tile, the rest recomputed); gen 5: producers decoupled from the MMA ring (every
-    A operand through the scratch, per-block accumulator drain; N < 512 falls back to gen 4)"""
+    A operand through the scratch, per-block accumulator drain; N < 512 falls back to gen 4); gen 6: two CTA pairs share a
+    candidate tile (N % 256 == 0 and N >= 1024, else gen 5)"""
     gp, ora = make(N, D, corr, corr_id)
     if isinstance(gen, tuple):
         gp.engine.set_replay(64, gen[1])
@@ -64,7 +66,7 @@ def test_rt_and_moments(N, D, corr, corr_id, gen):
     np.testing.assert_allclose(df, rt_ref @ ora.Ft.ravel(), rtol=0, atol=1e-4 * max(1.0, np.abs(ora.Ft).max()))
 
 
-@pytest.mark.parametrize("N,D,corr,corr_id", CASES[:4] + CASES[5:])
+@pytest.mark.parametrize("N,D,corr,corr_id", CASES[:4] + CASES[5:6])
 def test_fast_predict_tolerance(N, D, corr, corr_id):
     """predict() on the tensor-core path (three split-fp16 products per MAC, fp32 cross-correlation): the stated
     tolerance is PER FIT -- the a-priori half-widths b200bo_get_band_info reports (dy_model; ds_abs_3 + ds_rel_3
