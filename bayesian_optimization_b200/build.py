@@ -39,7 +39,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     srcs = sources()
     if force or not _newer(LIB, srcs):
-        cmd = [nvcc, *NVCC_FLAGS, "-o", LIB, os.path.join(CSRC, "b200bo.cu")]
+        dev = ["-DB200BO_DEV_KERNELS"] if os.environ.get("B200BO_DEV_KERNELS") == "1" else []  # + the superseded generations 2, 3
+        cmd = [nvcc, *NVCC_FLAGS, *dev, "-o", LIB, os.path.join(CSRC, "b200bo.cu")]
         r = subprocess.run(cmd, capture_output=True, text=True)
         log = r.stdout + r.stderr
         with open(os.path.join(HERE, "build.log"), "w") as f:

@@ -495,6 +495,9 @@ int b200bo_create(int device, b200bo_handle* out) {
   // developer knobs (A/B runs): first-pass products and the mbarrier suspend hint of the fused kernels
   if (const char* e = getenv("B200BO_FAST_PRODUCTS")) h->fast_products = atoi(e) == 3 ? 3 : 1;
   if (const char* e = getenv("B200BO_FAST_KERNEL")) h->fast_kernel_pref = std::max(1, std::min(6, atoi(e)));
+#ifndef B200BO_DEV_KERNELS
+  if (h->fast_kernel_pref == 2 || h->fast_kernel_pref == 3) h->fast_kernel_pref = 4;
+#endif
   if (const char* e = getenv("B200BO_CHOL_LOOKAHEAD")) h->lookahead = std::max(0, std::min(2, atoi(e)));
   if (const char* e = getenv("B200BO_GRAPHS")) h->use_graphs = atoi(e) != 0;
   if (const char* e = getenv("B200BO_CHOL_TC")) { int v = atoi(e); h->chol_tc = (v == 7 || v == 8) ? v : 0; }
@@ -568,6 +571,9 @@ int b200bo_set_precision(b200bo_handle h, int prec) {
 int b200bo_set_fast_kernel(b200bo_handle h, int generation) {
   CHECK_ARG(h, "handle is NULL");
   CHECK_ARG(generation >= 1 && generation <= 6, "generation is 1 .. 6");
+#ifndef B200BO_DEV_KERNELS
+  CHECK_ARG(generation != 2 && generation != 3, "generations 2 and 3 are only in developer builds (-DB200BO_DEV_KERNELS)");
+#endif
   h->fast_kernel_pref = generation;
   h->fast_ready = false;
   h->fvec_ready = false;
@@ -1663,6 +1669,9 @@ static int ensure_fast_state(b200bo_handle h) {
   if ((rc = make_linv_map(&h->map_hi, h->Lh.p, ld))) return rc;
   if ((rc = make_linv_map(&h->map_lo, h->Ll.p, ld))) return rc;
   h->use_v2 = h->fast_kernel_pref >= 2 && h->corr != ABSEXP;
+#ifndef B200BO_DEV_KERNELS
+  if (h->num_sms % 2) h->use_v2 = false;  // the single-CTA Gram kernel (generation 2) is a developer-build kernel: generation 1 instead
+#endif
   if (h->use_v2) {
     CU_TRY(h->cmean.reserve(D));
     CU_TRY(cudaMemcpyAsync(h->cmean.p, h->xmean.data(), D * 8, cudaMemcpyHostToDevice, st));
@@ -1703,7 +1712,7 @@ static int ensure_fast_state(b200bo_handle h) {
           at[0].id = cudaLaunchAttributeClusterDimension;
           at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
           cfg.attrs = at; cfg.numAttrs = 1;
-          auto kern = fk6::predict_fused_shared_kernel<MATERN52, 1>;
+          auto kern = fk6::predict_fused_shared_kernel<MATERN52, 1, false>;
           CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fk6::SMEM6_BYTES));
           int ncl = 0;
           cudaError_t e = cudaOccupancyMaxActiveClusters(&ncl, kern, &cfg);
@@ -1797,12 +1806,16 @@ static int launch_fused(b200bo_handle h, const double* xc_dev, long long m, size
     const long long tiles = (m + fk::BM - 1) / fk::BM;
     const int grid = h->use_pair ? (int)std::min<long long>(h->num_sms, 2 * ((tiles + 1) / 2))
                                  : (int)std::min<long long>(h->num_sms, tiles);
+#ifdef B200BO_DEV_KERNELS  /* generations 2 and 3 are superseded: developer builds only (A/B runs) */
 #define FK3_LAUNCH(C)                                                                                               \
   do {                                                                                                             \
     auto kern = nprod == 1 ? fk3::predict_fused_pair_kernel<C, 1> : fk3::predict_fused_pair_kernel<C, 3>;           \
     CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fk3::SMEM_BYTES));              \
     kern<<<grid, fk2::NT2, fk3::SMEM_BYTES, h->stream>>>(h->pair_maps, a);                                          \
   } while (0)
+#else
+#define FK3_LAUNCH(C) return set_err(B200BO_E_STATE, "generation 3 of the fused kernel is only in developer builds (-DB200BO_DEV_KERNELS)")
+#endif
 #define FK4_LAUNCH(C)                                                                                               \
   do {                                                                                                             \
     auto kern = nprod == 1 ? fk4::predict_fused_replay_kernel<C, 1> : fk4::predict_fused_replay_kernel<C, 3>;       \
@@ -1816,12 +1829,16 @@ static int launch_fused(b200bo_handle h, const double* xc_dev, long long m, size
     CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fk3::SMEM_BYTES));              \
     kern<<<grid, fk2::NT2, fk3::SMEM_BYTES, h->stream>>>(h->replay_maps, a, ra);                                    \
   } while (0)
+#ifdef B200BO_DEV_KERNELS
 #define FK2_LAUNCH(C)                                                                                               \
   do {                                                                                                             \
     auto kern = nprod == 1 ? fk2::predict_fused_tc2_kernel<C, 1> : fk2::predict_fused_tc2_kernel<C, 3>;             \
     CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fk2::SMEM_BYTES));              \
     kern<<<grid, fk2::NT2, fk2::SMEM_BYTES, h->stream>>>(h->map2_hi, h->map2_lo, h->map2_xh, h->map2_xl, a);        \
   } while (0)
+#else
+#define FK2_LAUNCH(C) return set_err(B200BO_E_STATE, "generation 2 of the fused kernel is only in developer builds (-DB200BO_DEV_KERNELS)")
+#endif
     if (h->use_pair && h->use_replay && h->use_decoupled && h->use_shared) {
       h->last_gen = 6;
       fk4::ReplayArgs ra;
@@ -1855,7 +1872,8 @@ static int launch_fused(b200bo_handle h, const double* xc_dev, long long m, size
       sa.dead_hint = getenv("B200BO_GEN6_DEAD_HINT") ? atoi(getenv("B200BO_GEN6_DEAD_HINT")) : 0;
 #define FK6_LAUNCH(C)                                                                                               \
   do {                                                                                                             \
-    auto kern = nprod == 1 ? fk6::predict_fused_shared_kernel<C, 1> : fk6::predict_fused_shared_kernel<C, 3>;       \
+    auto kern = nprod == 1 ? fk6::predict_fused_shared_kernel<C, 1, false> : fk6::predict_fused_shared_kernel<C, 3, false>; \
+    if (C == MATERN52 && nprod == 1 && a.trace) kern = fk6::predict_fused_shared_kernel<MATERN52, 1, true>; /* developer timeline */ \
     CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fk6::SMEM6_BYTES));             \
     kern<<<grid6, fk6::NT6, fk6::SMEM6_BYTES, h->stream>>>(h->replay_maps, a, ra, sa);                              \
   } while (0)

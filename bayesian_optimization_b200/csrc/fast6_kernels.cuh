@@ -107,7 +107,7 @@ __device__ __forceinline__ uint32_t dead_after(const SidePlan& sp, uint32_t tl, 
   return tl * (uint32_t)sp.upt - (uint32_t)sp.ul + (kc < sp.ul ? (uint32_t)kc + 1u : 0u);
 }
 
-template <int CORR, int NPROD>
+template <int CORR, int NPROD, bool TRACE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT6, 1)
 predict_fused_shared_kernel(const __grid_constant__ fk4::ReplayMaps rmaps, const Fused2Args p, const fk4::ReplayArgs ra,
                             const ShareArgs sh) {
@@ -226,49 +226,85 @@ predict_fused_shared_kernel(const __grid_constant__ fk4::ReplayMaps rmaps, const
             asm volatile("fence.proxy.async.global;" ::: "memory");
             verified = n_bulk;
           }
-          for (int ci = 0; ci < kext / KC; ++ci, ++it) {
-            const int kc = ci < n_bulk ? (desc ? n_bulk - 1 - ci : ci) : ci;
+          // ---- replayed chunks under the diagonal blocks: ST uses per iteration with a compile-time stage (the TMA warp
+          // shares its scheduler with four producer warps: the fewer instructions per use, the further it stays ahead)
+          const int row_b1 = n0 + (int)rank * (NBA / 2), row_b2 = n0 + NBA + (int)rank * (NBB / 2);
+          const uint64_t pol_a = (s == n_super - 1 && sh.dead_hint) ? pol_dead : pol_norm;
+          const uint32_t bulk_bytes = a_bytes + (uint32_t)((BA_PLANE + (act_2 ? BB_PLANE : 0)) * PLANES);
+          const int srow0 = scr_row(0, 0), srow_step = PLANES * BM;
+          auto bulk = [&](const uint32_t stg, const uint32_t parity, const int kc) {
+            const int k0 = kc * KC;
+            mbar_wait_fast(BAR(BAR_EMPTY_ST + stg), parity, p.err, 1);
+            if (el && it >= (uint32_t)ST) st_release_cta(cons_cnt, it - ST + 1);
+            const uint32_t fb = full0 + 8u * stg;
+            const uint32_t da = sbase + OFF_A + stg * A_STRIDE;
+            const uint32_t dst = sbase + OFF_B + stg * B_STRIDE;
+            mbar_expect_tx_cluster_p(fb, bulk_bytes, el);
+            tma_load_2d_pair_hint(da, &rmaps.scr, 0, srow0 + kc * srow_step, fb, pol_a, el);
+            if (NPROD == 3) tma_load_2d_pair_hint(da + A_HALF_BYTES, &rmaps.scr, 0, srow0 + kc * srow_step + BM, fb, pol_a, el);
+            tma_load_2d_pair_hint(dst, &maps.hi128, k0, row_b1, fb, pol_keep, el);
+            if (NPROD == 3) tma_load_2d_pair_hint(dst + BOFF_A_LO, &maps.lo128, k0, row_b1, fb, pol_keep, el);
+            if (act_2) {
+              tma_load_2d_pair_hint(dst + BOFF_B_HI, &maps.hi64, k0, row_b2, fb, pol_keep, el);
+              if (NPROD == 3) tma_load_2d_pair_hint(dst + BOFF_B_LO, &maps.lo64, k0, row_b2, fb, pol_keep, el);
+            }
+            ++it;
+          };
+          int ci = 0;
+          const int kstep = desc ? -1 : 1;
+          int kc = desc ? n_bulk - 1 : 0;
+          while (ci < n_bulk && st != 0) {
+            bulk(st, ph ^ 1u, kc);
+            st = (st + 1) & (ST - 1);
+            ph ^= (st == 0);
+            ++ci;
+            kc += kstep;
+          }
+          while (ci + ST <= n_bulk) {   // st == 0 here
+#pragma unroll
+            for (int stg = 0; stg < ST; ++stg) bulk((uint32_t)stg, ph ^ 1u, kc + stg * kstep);
+            ph ^= 1u;
+            ci += ST;
+            kc += ST * kstep;
+          }
+          while (ci < n_bulk) {
+            bulk(st, ph ^ 1u, kc);
+            st = (st + 1) & (ST - 1);
+            ph ^= (st == 0);
+            ++ci;
+            kc += kstep;
+          }
+          // ---- diagonal chunks (ascending): first touch of a chunk by this side waits for its producer
+          for (; ci < kext / KC; ++ci, ++it) {
+            const int kc = ci;
             const int k0 = kc * KC;
             mbar_wait_fast(BAR(BAR_EMPTY_ST + st), ph ^ 1, p.err, 1);
             if (el && it >= (uint32_t)ST) st_release_cta(cons_cnt, it - ST + 1);
             const uint32_t fb = full0 + 8u * st;
             const uint32_t da = sbase + OFF_A + st * A_STRIDE;
             const uint32_t dst = sbase + OFF_B + st * B_STRIDE;
-            if (k0 < n0 && act_2) {
-              const uint64_t pol_a = (s == n_super - 1 && sh.dead_hint) ? pol_dead : pol_norm;
-              mbar_expect_tx_cluster_p(fb, a_bytes + (uint32_t)((BA_PLANE + BB_PLANE) * PLANES), el);
-              tma_load_2d_pair_hint(da, &rmaps.scr, 0, scr_row(kc, 0), fb, pol_a, el);
-              if (NPROD == 3) tma_load_2d_pair_hint(da + A_HALF_BYTES, &rmaps.scr, 0, scr_row(kc, 1), fb, pol_a, el);
-              tma_load_2d_pair_hint(dst, &maps.hi128, k0, n0 + (int)rank * (NBA / 2), fb, pol_keep, el);
-              if (NPROD == 3) tma_load_2d_pair_hint(dst + BOFF_A_LO, &maps.lo128, k0, n0 + (int)rank * (NBA / 2), fb, pol_keep, el);
-              tma_load_2d_pair_hint(dst + BOFF_B_HI, &maps.hi64, k0, n0 + NBA + (int)rank * (NBB / 2), fb, pol_keep, el);
-              if (NPROD == 3) tma_load_2d_pair_hint(dst + BOFF_B_LO, &maps.lo64, k0, n0 + NBA + (int)rank * (NBB / 2), fb, pol_keep, el);
-            } else {
-              if (kc >= verified) {  // first touch of this chunk in this tile by this side
-                wait_chunk(kc, tl);
-                asm volatile("fence.proxy.async.global;" ::: "memory");
-                verified = kc + 1;
-              }
-              const bool act_01 = k0 < n0 + 128;
-              const bool act_1 = !act_01 && k0 < n0 + 256;
-              const uint32_t bbytes = (uint32_t)((act_01 ? BA_PLANE : 0) + (act_1 ? BB_PLANE : 0) + (act_2 ? BB_PLANE : 0)) * (uint32_t)PLANES;
-              mbar_expect_tx_cluster_p(fb, bbytes + a_bytes, el);
-              tma_load_2d_pair_p(da, &rmaps.scr, 0, scr_row(kc, 0), fb, el);
-              if (NPROD == 3) tma_load_2d_pair_p(da + A_HALF_BYTES, &rmaps.scr, 0, scr_row(kc, 1), fb, el);
-              if (act_01) {
-                const int row0 = n0 + (int)rank * (NBA / 2);
-                tma_load_2d_pair_p(dst, &maps.hi128, k0, row0, fb, el);
-                if (NPROD == 3) tma_load_2d_pair_p(dst + BOFF_A_LO, &maps.lo128, k0, row0, fb, el);
-              } else if (act_1) {
-                const int row0 = n0 + 128 + (int)rank * 64;
-                tma_load_2d_pair_p(dst, &maps.hi64, k0, row0, fb, el);
-                if (NPROD == 3) tma_load_2d_pair_p(dst + BOFF_A_LO, &maps.lo64, k0, row0, fb, el);
-              }
-              if (act_2) {
-                const int row0 = n0 + NBA + (int)rank * (NBB / 2);
-                tma_load_2d_pair_p(dst + BOFF_B_HI, &maps.hi64, k0, row0, fb, el);
-                if (NPROD == 3) tma_load_2d_pair_p(dst + BOFF_B_LO, &maps.lo64, k0, row0, fb, el);
-              }
+            if (kc >= verified) {
+              wait_chunk(kc, tl);
+              asm volatile("fence.proxy.async.global;" ::: "memory");
+              verified = kc + 1;
+            }
+            const bool act_01 = k0 < n0 + 128;
+            const bool act_1 = !act_01 && k0 < n0 + 256;
+            const uint32_t bbytes = (uint32_t)((act_01 ? BA_PLANE : 0) + (act_1 ? BB_PLANE : 0) + (act_2 ? BB_PLANE : 0)) * (uint32_t)PLANES;
+            mbar_expect_tx_cluster_p(fb, bbytes + a_bytes, el);
+            tma_load_2d_pair_p(da, &rmaps.scr, 0, scr_row(kc, 0), fb, el);
+            if (NPROD == 3) tma_load_2d_pair_p(da + A_HALF_BYTES, &rmaps.scr, 0, scr_row(kc, 1), fb, el);
+            if (act_01) {
+              tma_load_2d_pair_p(dst, &maps.hi128, k0, row_b1, fb, el);
+              if (NPROD == 3) tma_load_2d_pair_p(dst + BOFF_A_LO, &maps.lo128, k0, row_b1, fb, el);
+            } else if (act_1) {
+              const int row0 = n0 + 128 + (int)rank * 64;
+              tma_load_2d_pair_p(dst, &maps.hi64, k0, row0, fb, el);
+              if (NPROD == 3) tma_load_2d_pair_p(dst + BOFF_A_LO, &maps.lo64, k0, row0, fb, el);
+            }
+            if (act_2) {
+              tma_load_2d_pair_p(dst + BOFF_B_HI, &maps.hi64, k0, row_b2, fb, el);
+              if (NPROD == 3) tma_load_2d_pair_p(dst + BOFF_B_LO, &maps.lo64, k0, row_b2, fb, el);
             }
             st = (st + 1) & (ST - 1);
             ph ^= (st == 0);
@@ -354,10 +390,9 @@ predict_fused_shared_kernel(const __grid_constant__ fk4::ReplayMaps rmaps, const
       uint32_t n_my = 0;
       for (long long pt = group; pt < n_ptiles; pt += n_groups) ++n_my;
       uint32_t left = n_my * (uint32_t)me.upt;
-      uint32_t ist = 0, st = 0, ph = 0;
+      uint32_t ist = 0, st = 0, ph = 0, ic = 0;
       if (left) mbar_wait(BAR(BAR_FULL + 0), 0, p.err, 3);
       for (long long pt = group; pt < n_ptiles; pt += n_groups) {
-        int idx = 0;
         for (int s = 0; s < n_super; ++s) {
           if (!((me.mine >> s) & 1u)) continue;
           const int kext = min(ld, WC * (s + 1));
@@ -365,31 +400,90 @@ predict_fused_shared_kernel(const __grid_constant__ fk4::ReplayMaps rmaps, const
           const bool has2 = n0 + NBA < ld;
           const uint32_t pe = (ist & 1) ^ 1;
           const int n_bulk = n0 / KC;
-          const bool desc = ((me.n - 1 - idx) & 1) != 0;
-          ++idx;
-          for (int ci = 0; ci < kext / KC; ++ci) {
-            const int k0 = (ci < n_bulk ? (desc ? n_bulk - 1 - ci : ci) : ci) * KC;
+          // The issuer is paced by the LENGTH of its own instruction stream whenever the producers share its scheduler
+          // (developer timeline, profiles/r02/trace_gen6_*: 1190 clk per chunk use in a side's last super-tile against
+          // 815 clk while the producers idle; ~100 SASS instructions per chunk use, 39 of them loop-header index
+          // arithmetic and 20 R2UR moves of descriptors that lived in vector registers).  So: the order of the replayed
+          // chunks is the TMA warp's business only (every chunk under the diagonal blocks takes the same MMAs), and the
+          // bulk of a super-tile runs ST chunk uses per iteration with the stage a COMPILE-TIME constant -- descriptors
+          // are then uniform-register adds of an immediate.
+          const int nuse = kext / KC;
+          // ---- general chunk use: first of the super-tile (overwrites the accumulators), diagonal chunks
+          auto general = [&](int ci) {
+            const int k0 = ci < n_bulk ? 0 : ci * KC;     // any chunk under the diagonal blocks behaves like k0 = 0
             const bool first = ci == 0;
             const uint32_t nst = (st + 1) & (ST - 1), nph = ph ^ (nst == 0 ? 1u : 0u);
+            const bool tr = TRACE && p.trace && blockIdx.x == 0 && ic < (uint32_t)TRACE5_CHUNKS && lane == 0;
+            if (tr) p.trace[ic * 8 + 0] = clock64();
             const uint64_t da_hi = da0 + A_STEP * st, da_lo = da_hi + (A_HALF_BYTES >> 4);
             const uint64_t db_hi = db0 + B_STEP * st, db_lo = db_hi + (BOFF_A_LO >> 4);
             const uint64_t db2_hi = db_hi + (BOFF_B_HI >> 4), db2_lo = db_hi + (BOFF_B_LO >> 4);
             --left;
-            if (!first && k0 < n0 && has2) {
-              tc_fence_after();
-              if (el) {
+            if (first) {
+              mbar_wait(BAR(BAR_ACC_EMPTY + 0), pe, p.err, 2);
+              mbar_wait(BAR(BAR_ACC_EMPTY + 1), pe, p.err, 2);
+            }
+            tc_fence_after();
+            if (tr) p.trace[ic * 8 + 1] = clock64();
+            if (k0 < n0 + NBA) {
+              const bool both = k0 < n0 + 128;
+              const uint32_t td = tmem_base + (both ? 0u : 128u);
+              const uint32_t idesc = both ? idesc_256 : idesc_128;
 #pragma unroll
-                for (int ks = 0; ks < KC / 16; ++ks) {
-                  const uint64_t o = (uint64_t)(ks * 2);
-                  umma_f16_pair(tmem_base, da_hi + o, db_hi + o, idesc_256, 1);
-                  if (NPROD == 3) {
-                    umma_f16_pair(tmem_base, da_hi + o, db_lo + o, idesc_256, 1);
-                    umma_f16_pair(tmem_base, da_lo + o, db_hi + o, idesc_256, 1);
-                  }
+              for (int ks = 0; ks < KC / 16; ++ks) {
+                const uint64_t o = (uint64_t)(ks * 2);
+                umma_f16_pair_p(td, da_hi + o, db_hi + o, idesc, !first || ks != 0, el);
+                if (NPROD == 3) {
+                  umma_f16_pair_p(td, da_hi + o, db_lo + o, idesc, 1, el);
+                  umma_f16_pair_p(td, da_lo + o, db_hi + o, idesc, 1, el);
                 }
               }
-              if (left) mbar_wait_fast(BAR(BAR_FULL + nst), nph, p.err, 3);
-              if (el) {
+              if (k0 + KC == min(n0 + 128, kext)) umma_commit_pair_p(BAR(BAR_ACC_FULL + 0), el);
+              if (k0 + KC == min(n0 + 256, kext)) umma_commit_pair_p(BAR(BAR_ACC_FULL + 1), el);
+            }
+            if (left) mbar_wait_fast(BAR(BAR_FULL + nst), nph, p.err, 3);
+            if (has2) {
+              if (first) mbar_wait(BAR(BAR_ACC_EMPTY + 2), pe, p.err, 2);
+              tc_fence_after();
+#pragma unroll
+              for (int ks = 0; ks < KC / 16; ++ks) {
+                const uint64_t o = (uint64_t)(ks * 2);
+                umma_f16_pair_p(tmem_base + (uint32_t)NBA, da_hi + o, db2_hi + o, idesc_128, !first || ks != 0, el);
+                if (NPROD == 3) {
+                  umma_f16_pair_p(tmem_base + (uint32_t)NBA, da_hi + o, db2_lo + o, idesc_128, 1, el);
+                  umma_f16_pair_p(tmem_base + (uint32_t)NBA, da_lo + o, db2_hi + o, idesc_128, 1, el);
+                }
+              }
+            }
+            umma_commit_pair_p(BAR(BAR_EMPTY_ST + st), el);
+            if (tr) p.trace[ic * 8 + 2] = clock64();
+            ++ic;
+            st = nst;
+            ph = nph;
+          };
+          // ---- one replayed chunk under the diagonal blocks; stage `stg` (compile-time in the unrolled loop below)
+          auto bulk = [&](const uint32_t stg, const uint32_t wait_parity) {
+            const bool tr = TRACE && p.trace && blockIdx.x == 0 && ic < (uint32_t)TRACE5_CHUNKS && lane == 0;
+            if (tr) p.trace[ic * 8 + 0] = clock64();
+            const uint64_t da_hi = da0 + A_STEP * stg, da_lo = da_hi + (A_HALF_BYTES >> 4);
+            const uint64_t db_hi = db0 + B_STEP * stg, db_lo = db_hi + (BOFF_A_LO >> 4);
+            const uint64_t db2_hi = db_hi + (BOFF_B_HI >> 4), db2_lo = db_hi + (BOFF_B_LO >> 4);
+            --left;
+            tc_fence_after();
+            if (el) {
+#pragma unroll
+              for (int ks = 0; ks < KC / 16; ++ks) {
+                const uint64_t o = (uint64_t)(ks * 2);
+                umma_f16_pair(tmem_base, da_hi + o, db_hi + o, idesc_256, 1);
+                if (NPROD == 3) {
+                  umma_f16_pair(tmem_base, da_hi + o, db_lo + o, idesc_256, 1);
+                  umma_f16_pair(tmem_base, da_lo + o, db_hi + o, idesc_256, 1);
+                }
+              }
+            }
+            if (left) mbar_wait_fast(BAR(BAR_FULL + ((stg + 1) & (ST - 1))), wait_parity, p.err, 3);
+            if (el) {
+              if (has2) {
 #pragma unroll
                 for (int ks = 0; ks < KC / 16; ++ks) {
                   const uint64_t o = (uint64_t)(ks * 2);
@@ -399,49 +493,35 @@ predict_fused_shared_kernel(const __grid_constant__ fk4::ReplayMaps rmaps, const
                     umma_f16_pair(tmem_base + (uint32_t)NBA, da_lo + o, db2_hi + o, idesc_128, 1);
                   }
                 }
-                umma_commit_pair(BAR(BAR_EMPTY_ST + st));
               }
-            } else {
-              if (first) {
-                mbar_wait(BAR(BAR_ACC_EMPTY + 0), pe, p.err, 2);
-                mbar_wait(BAR(BAR_ACC_EMPTY + 1), pe, p.err, 2);
-              }
-              tc_fence_after();
-              if (k0 < n0 + NBA) {
-                const bool both = k0 < n0 + 128;
-                const uint32_t td = tmem_base + (both ? 0u : 128u);
-                const uint32_t idesc = both ? idesc_256 : idesc_128;
-#pragma unroll
-                for (int ks = 0; ks < KC / 16; ++ks) {
-                  const uint64_t o = (uint64_t)(ks * 2);
-                  umma_f16_pair_p(td, da_hi + o, db_hi + o, idesc, !first || ks != 0, el);
-                  if (NPROD == 3) {
-                    umma_f16_pair_p(td, da_hi + o, db_lo + o, idesc, 1, el);
-                    umma_f16_pair_p(td, da_lo + o, db_hi + o, idesc, 1, el);
-                  }
-                }
-                if (k0 + KC == min(n0 + 128, kext)) umma_commit_pair_p(BAR(BAR_ACC_FULL + 0), el);
-                if (k0 + KC == min(n0 + 256, kext)) umma_commit_pair_p(BAR(BAR_ACC_FULL + 1), el);
-              }
-              if (left) mbar_wait_fast(BAR(BAR_FULL + nst), nph, p.err, 3);
-              if (has2) {
-                if (first) mbar_wait(BAR(BAR_ACC_EMPTY + 2), pe, p.err, 2);
-                tc_fence_after();
-#pragma unroll
-                for (int ks = 0; ks < KC / 16; ++ks) {
-                  const uint64_t o = (uint64_t)(ks * 2);
-                  umma_f16_pair_p(tmem_base + (uint32_t)NBA, da_hi + o, db2_hi + o, idesc_128, !first || ks != 0, el);
-                  if (NPROD == 3) {
-                    umma_f16_pair_p(tmem_base + (uint32_t)NBA, da_hi + o, db2_lo + o, idesc_128, 1, el);
-                    umma_f16_pair_p(tmem_base + (uint32_t)NBA, da_lo + o, db2_hi + o, idesc_128, 1, el);
-                  }
-                }
-              }
-              umma_commit_pair_p(BAR(BAR_EMPTY_ST + st), el);
+              umma_commit_pair(BAR(BAR_EMPTY_ST + stg));
             }
+            if (tr) p.trace[ic * 8 + 2] = clock64();
+            ++ic;
+          };
+          auto bulk_rt = [&]() {   // runtime stage: the few uses that bring the ring back to stage 0 / the remainder
+            const uint32_t nst = (st + 1) & (ST - 1), nph = ph ^ (nst == 0 ? 1u : 0u);
+            bulk(st, nph);
             st = nst;
             ph = nph;
+          };
+          int ci = 0;
+          general(ci++);
+          while (ci < n_bulk && st != 0) {
+            bulk_rt();
+            ++ci;
           }
+          while (ci + ST <= n_bulk) {   // st == 0 here
+#pragma unroll
+            for (int stg = 0; stg < ST; ++stg) bulk((uint32_t)stg, stg == ST - 1 ? ph ^ 1u : ph);
+            ph ^= 1u;
+            ci += ST;
+          }
+          while (ci < n_bulk) {
+            bulk_rt();
+            ++ci;
+          }
+          for (; ci < nuse; ++ci) general(ci);
           if (!has2) {
             mbar_wait(BAR(BAR_ACC_EMPTY + 2), pe, p.err, 2);
           }
@@ -543,9 +623,12 @@ predict_fused_shared_kernel(const __grid_constant__ fk4::ReplayMaps rmaps, const
         if ((lc & 1) != grp) continue;  // the other group's chunk (nmy is even: chunk parity = j parity)
         const int kc = my_chunk(lc);
         const uint32_t ax = j % AUX_STAGES;
+        const bool tr = TRACE && p.trace && blockIdx.x == 0 && j < (uint32_t)TRACE5_CHUNKS && pw == 0 && lane == 0;
+        if (tr) p.trace[j * 8 + 3] = clock64();
         mbar_wait(BAR(BAR_FULL_AUX + ax), (j / AUX_STAGES) & 1, p.err, 11);
         mbar_wait(BAR(BAR_FULL_G + grp), (j / 2) & 1, p.err, 10);
         tc_fence_after();
+        if (tr) p.trace[j * 8 + 4] = clock64();
         float ysum = 0.f, fsum = 0.f;
         uint32_t gr0[16], gr1[16];
         fk2::tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(G_COL0 + KC * grp + 32 * ch), gr0);
@@ -560,6 +643,7 @@ predict_fused_shared_kernel(const __grid_constant__ fk4::ReplayMaps rmaps, const
         if (grp == 0) asm volatile("bar.sync 1, %0;" ::"n"(32 * NPW / 2) : "memory");
         else asm volatile("bar.sync 2, %0;" ::"n"(32 * NPW / 2) : "memory");
         if (elected) mbar_arrive_leader(BAR(BAR_EMPTY_G + grp), leader);
+        if (tr) p.trace[j * 8 + 5] = clock64();
         uint8_t* g_hi = scr + ((size_t)scr_row(kc, 0) + (size_t)m) * 128;
         uint8_t* g_lo = scr + ((size_t)scr_row(kc, PLANES - 1) + (size_t)m) * 128;
 #pragma unroll
@@ -604,8 +688,10 @@ predict_fused_shared_kernel(const __grid_constant__ fk4::ReplayMaps rmaps, const
         ysum_d += (double)ysum;
         fsum_d += (double)fsum;
         asm volatile("fence.proxy.async.global;" ::: "memory");  // scratch stores -> visible to the TMA loads
+        if (tr) p.trace[j * 8 + 6] = clock64();
         if (grp == 0) asm volatile("bar.sync 1, %0;" ::"n"(32 * NPW / 2) : "memory");
         else asm volatile("bar.sync 2, %0;" ::"n"(32 * NPW / 2) : "memory");
+        if (tr) p.trace[j * 8 + 7] = clock64();
         ++done;
         if (elected) {
           st_release_cta(prod_cnt + 4u * (uint32_t)grp, done);

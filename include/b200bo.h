@@ -112,7 +112,9 @@ int b200bo_set_keep_R(b200bo_handle h, int keep);
  * 4 = CTA pairs + replay of r from an L2-resident scratch, first uses written straight into the A ring;
  * 3 = CTA pairs (tcgen05 cta_group::2) sharing the B operands, r recomputed per accumulator super-tile;
  * 2 = single-CTA kernel with the Gram product on the tensor cores; both need a kernel that is a function of the L2
- * distance, else generation 1 runs; 1 = always the first-generation kernel (A/B comparisons) */
+ * distance, else generation 1 runs; 1 = always the first-generation kernel (A/B comparisons).  Generations 2 and 3 are
+ * superseded and only compiled into developer builds (B200BO_DEV_KERNELS=1 python -m bayesian_optimization_b200.build):
+ * a product build answers B200BO_E_ARG for them. */
 int b200bo_set_fast_kernel(b200bo_handle h, int generation);
 /* generation 4 only: the fp16 cross-correlation chunks r[:, k:k+64] of a candidate tile are computed once, kept in a
  * per-SM scratch of at most budget_mb MB in total (default 64: it has to stay in L2 next to the fp16 L^-1) and replayed

@@ -20,9 +20,9 @@ for N, D, M in [(70, 3, 37), (200, 5, 300), (600, 4, 300)]:
         _, _, ydx, mdx = gp.engine.gradient(Xc)
         v, dx = b2.EI(model=gp).value_and_gradient(Xc)
         print("grad", float(np.abs(g).max()), float(np.abs(ydx).max()), float(np.abs(dx).max()))
-        # tensor-core flavour: generations 3, 4 (partial replay) and 5 (N >= 512) of the fused kernel, one and three products
+        # tensor-core flavour: generations 4 (partial replay), 5 (N >= 512) and 6 (N % 256 == 0, N >= 1024) of the fused kernel
         gp.engine.set_precision(_lib.PREC_FAST)
-        for gen in (3, 4, 5):
+        for gen in (4, 5, 6):
             gp.engine.set_fast_kernel(gen)
             if gen == 4:
                 gp.engine.set_replay(64, 2)

@@ -48,7 +48,12 @@ def test_rt_and_moments(N, D, corr, corr_id, gen):
     if isinstance(gen, tuple):
         gp.engine.set_replay(64, gen[1])
         gen = gen[0]
-    gp.engine.set_fast_kernel(gen)
+    try:
+        gp.engine.set_fast_kernel(gen)
+    except _lib.B200BOError as e:   # generations 2 and 3 are superseded: developer builds only (B200BO_DEV_KERNELS=1)
+        if gen in (2, 3) and "developer builds" in str(e):
+            pytest.skip(str(e))
+        raise
     M = 300  # ragged: not a multiple of the 128-row tile
     Xc = workloads.canonical_candidates(M, D)
     rt, yh, ss, df = gp.engine.debug_fast_rt(Xc)
