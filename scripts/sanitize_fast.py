@@ -1,5 +1,5 @@
-"""small tensor-core passes (generation 5 at N = 600, generations 3 / 4 below 512; the int8 trailing update) for
-compute-sanitizer --tool racecheck / synccheck"""
+"""small tensor-core passes (generation 6 at N = 1024, generation 5 at N = 600, generation 4 below 512; the int8 trailing
+update) for compute-sanitizer --tool memcheck / racecheck / synccheck"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -7,7 +7,7 @@ import bayesian_optimization_b200 as b2
 from bayesian_optimization_b200 import _lib
 
 rng = np.random.default_rng(0)
-for N, D, M in [(200, 5, 300), (600, 4, 600)]:
+for N, D, M in [(200, 5, 300), (600, 4, 600), (1024, 4, 700)]:
     X = rng.uniform(0, 1, (N, D)); y = np.sin(3 * X).sum(axis=1) + 0.3 * rng.standard_normal(N)
     gp = b2.GaussianProcess(mean=b2.constant_trend(D), corr="matern52", thetaL=[1e-5] * D, thetaU=[1e2] * D, nugget=1e-4)
     gp._check_data(X, y)
