@@ -23,6 +23,7 @@
 #include "fast5_kernels.cuh"
 #include "fast6_kernels.cuh"
 #include "fit_kernels.cuh"
+#include "assemble_kernels.cuh"
 #include "grad_kernels.cuh"
 #include "host_qr.h"
 #include "oz_kernels.cuh"
@@ -202,7 +203,7 @@ struct b200bo_ctx {
   bool use_decoupled = false;
   bool use_shared = false;    // generation 6 applies to this fit (ld % 256 == 0, ld >= 1024, all CTAs co-resident)
   int shared_ok = -1;         // occupancy query of generation 6: -1 not asked yet, 0 no, 1 yes
-  DevBuf<uint32_t> share_flags;
+  DevBuf<uint32_t> share_flags, smid_dbg;
   int last_gen = 0;           // generation of the fused kernel the last tensor-core launch used (timings[10])
   cudaStream_t copy_stream = nullptr;
   cudaStream_t la_stream = nullptr;  // low-priority helper stream of the Cholesky look-ahead
@@ -249,6 +250,11 @@ struct b200bo_ctx {
   const void* oz_map_base = nullptr;
   int oz_map_rcap = 0;
   bool oz_attr = false;
+  // TMA-staged kernel-matrix assembly (assemble_kernels.cuh)
+  int assemble_tma = 1;           // B200BO_ASSEMBLE_TMA=0: the first version (fit_kernels.cuh)
+  CUtensorMap mapXt;
+  const void* mapXt_base = nullptr;
+  int mapXt_ld = 0, mapXt_D = 0;
 };
 
 namespace {
@@ -500,6 +506,7 @@ int b200bo_create(int device, b200bo_handle* out) {
 #endif
   if (const char* e = getenv("B200BO_CHOL_LOOKAHEAD")) h->lookahead = std::max(0, std::min(2, atoi(e)));
   if (const char* e = getenv("B200BO_GRAPHS")) h->use_graphs = atoi(e) != 0;
+  if (const char* e = getenv("B200BO_ASSEMBLE_TMA")) h->assemble_tma = atoi(e) != 0;
   if (const char* e = getenv("B200BO_CHOL_TC")) { int v = atoi(e); h->chol_tc = (v == 7 || v == 8) ? v : 0; }
   if (const char* e = getenv("B200BO_CHOL_TC_MIN_ROWS")) h->chol_tc_min_rows = std::max(64, atoi(e));
   if (const char* e = getenv("B200BO_REPLAY_MB")) h->replay_mb = std::max(0, std::min(4096, atoi(e)));
@@ -772,9 +779,34 @@ static int factor_impl(b200bo_handle h, int corr, const double* theta, int n_the
     a.sigma2 = mode == B200BO_MODE_NOISY ? par_last : 0.0;
     a.noise_var = mode == B200BO_MODE_NOISY ? noise_var : 0.0;
     a.alpha = mode == B200BO_MODE_NOISE_ESTIM ? par_last : 1.0;
-    size_t smem = ((size_t)2 * D * NB + ((D + 1) & ~1) + NB * 66) * sizeof(double);
-    CU_TRY(cudaFuncSetAttribute(kmat_assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kmat_assemble_kernel<<<nb * (nb + 1) / 2, 256, smem, st>>>(a);
+    if (h->assemble_tma && D <= KA_DMAX) {
+      // TMA-staged version (assemble_kernels.cuh): the (D, 64) slabs of Xt by cp.async.bulk.tensor, 256-bit stores
+      if (h->mapXt_base != h->Xt.p || h->mapXt_ld != ld || h->mapXt_D != D) {
+        int rc = make_map_2d(&h->mapXt, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, h->Xt.p, (uint64_t)ld, (uint64_t)D, (uint64_t)ld * 8, NB, D,
+                             CU_TENSOR_MAP_SWIZZLE_NONE);
+        if (rc) return rc;
+        h->mapXt_base = h->Xt.p; h->mapXt_ld = ld; h->mapXt_D = D;
+      }
+      const size_t smem = ((size_t)2 * D * NB + D + 2) * sizeof(double);
+#define KA_LAUNCH(C)                                                                                                    \
+  do {                                                                                                                  \
+    if (smem > 48 * 1024) CU_TRY(cudaFuncSetAttribute(kmat_assemble_tma_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    kmat_assemble_tma_kernel<C><<<nb * (nb + 1) / 2, 256, smem, st>>>(h->mapXt, a);                                       \
+  } while (0)
+      switch (corr) {
+        case RBF: KA_LAUNCH(RBF); break;
+        case MATERN12: KA_LAUNCH(MATERN12); break;
+        case MATERN32: KA_LAUNCH(MATERN32); break;
+        case MATERN52: KA_LAUNCH(MATERN52); break;
+        case ABSEXP: KA_LAUNCH(ABSEXP); break;
+        default: KA_LAUNCH(-1); break;  // cubic, generalized_exponential, general-nu Matern
+      }
+#undef KA_LAUNCH
+    } else {
+      size_t smem = ((size_t)2 * D * NB + ((D + 1) & ~1) + NB * 66) * sizeof(double);
+      CU_TRY(cudaFuncSetAttribute(kmat_assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kmat_assemble_kernel<<<nb * (nb + 1) / 2, 256, smem, st>>>(a);
+    }
     CU_TRY(cudaGetLastError());
     ++launches;
     if (h->keepR) CU_TRY(cudaMemcpyAsync(h->Rkeep.p, h->A.p, nn * 8, cudaMemcpyDeviceToDevice, st));
@@ -1870,6 +1902,11 @@ static int launch_fused(b200bo_handle h, const double* xc_dev, long long m, size
       sa.flags = h->share_flags.p;
       sa.side_mask = mask;
       sa.dead_hint = getenv("B200BO_GEN6_DEAD_HINT") ? atoi(getenv("B200BO_GEN6_DEAD_HINT")) : 0;
+      sa.smid_out = nullptr;
+      if (getenv("B200BO_SMID_DUMP")) {  // developer: where did the CTAs land?
+        CU_TRY(h->smid_dbg.reserve(h->num_sms));
+        sa.smid_out = h->smid_dbg.p;
+      }
 #define FK6_LAUNCH(C)                                                                                               \
   do {                                                                                                             \
     auto kern = nprod == 1 ? fk6::predict_fused_shared_kernel<C, 1, false> : fk6::predict_fused_shared_kernel<C, 3, false>; \
@@ -1884,6 +1921,15 @@ static int launch_fused(b200bo_handle h, const double* xc_dev, long long m, size
         default: FK6_LAUNCH(MATERN52); break;
       }
 #undef FK6_LAUNCH
+      if (sa.smid_out) {
+        std::vector<uint32_t> sm(grid6);
+        CU_TRY(cudaMemcpyAsync(sm.data(), sa.smid_out, grid6 * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+        CU_TRY(cudaStreamSynchronize(h->stream));
+        if (FILE* f = fopen(getenv("B200BO_SMID_DUMP"), "w")) {
+          for (int i = 0; i < grid6; ++i) fprintf(f, "%d %u\n", i, sm[i]);
+          fclose(f);
+        }
+      }
     } else if (h->use_pair && h->use_replay && h->use_decoupled) {
       h->last_gen = 5;
       fk4::ReplayArgs ra;

@@ -50,6 +50,7 @@ struct ShareArgs {
   uint32_t* flags;     // (groups, 2 ranks, 2 sides, 3 counters) x 8 words (one 32-byte sector per counter), zeroed per launch
   uint32_t side_mask;  // bit s = side that owns accumulator super-tile s
   int dead_hint;       // 1: the last replay of a chunk is loaded with L2::evict_first (generation 5's habit)
+  uint32_t* smid_out;  // NULL, or (gridDim.x,): the SM every CTA ran on (developer: placement of the partner pairs)
 };
 
 __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
@@ -149,6 +150,11 @@ predict_fused_shared_kernel(const __grid_constant__ fk4::ReplayMaps rmaps, const
   // chunk index of this side's lc-th chunk: pairs (0,1), (4,5), ... for side 0, (2,3), (6,7), ... for side 1
   auto my_chunk = [&](int lc) { return ((lc >> 1) << 2) + ((int)side << 1) + (lc & 1); };
 
+  if (threadIdx.x == 0 && sh.smid_out) {
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    sh.smid_out[blockIdx.x] = smid;
+  }
   if (threadIdx.x == 0) {
     if ((sbase & 1023u) || ra.n_store < nch || nch < 16 || (nch & 3) || me.n == 0 || ot.n == 0) {
       atomicExch(p.err, 97);
