@@ -204,6 +204,7 @@ struct b200bo_ctx {
   bool use_shared = false;    // generation 6 applies to this fit (ld % 256 == 0, ld >= 1024, all CTAs co-resident)
   int shared_ok = -1;         // occupancy query of generation 6: -1 not asked yet, 0 no, 1 yes
   DevBuf<uint32_t> share_flags, smid_dbg;
+  int gen6_min_ld = 4096;     // smallest padded N generation 6 is used for (B200BO_GEN6_MIN_LD)
   int last_gen = 0;           // generation of the fused kernel the last tensor-core launch used (timings[10])
   cudaStream_t copy_stream = nullptr;
   cudaStream_t la_stream = nullptr;  // low-priority helper stream of the Cholesky look-ahead
@@ -506,6 +507,7 @@ int b200bo_create(int device, b200bo_handle* out) {
 #endif
   if (const char* e = getenv("B200BO_CHOL_LOOKAHEAD")) h->lookahead = std::max(0, std::min(2, atoi(e)));
   if (const char* e = getenv("B200BO_GRAPHS")) h->use_graphs = atoi(e) != 0;
+  if (const char* e = getenv("B200BO_GEN6_MIN_LD")) h->gen6_min_ld = std::max(1024, atoi(e));
   if (const char* e = getenv("B200BO_ASSEMBLE_TMA")) h->assemble_tma = atoi(e) != 0;
   if (const char* e = getenv("B200BO_CHOL_TC")) { int v = atoi(e); h->chol_tc = (v == 7 || v == 8) ? v : 0; }
   if (const char* e = getenv("B200BO_CHOL_TC_MIN_ROWS")) h->chol_tc_min_rows = std::max(64, atoi(e));
@@ -1735,7 +1737,9 @@ static int ensure_fast_state(b200bo_handle h) {
       const size_t n_halves = h->use_decoupled ? want : std::min(want, cap);
       h->use_replay = h->fast_kernel_pref >= 4 && n_halves >= (size_t)h->num_sms * 2 * blk;
       h->use_shared = false;
-      if (h->fast_kernel_pref >= 6 && h->use_decoupled && ld % 256 == 0 && ld >= 1024 && h->num_sms % 4 == 0) {
+      // generation 6 pays where a tile is long: N = 4096 + 4 - 6 %, N <= 2048 slower than generation 5 (the hand-over between
+      // the two sides costs a fixed ~3 us per chunk class and tile; profiles/r02/gen6_vs_gen5_by_N.txt)
+      if (h->fast_kernel_pref >= 6 && h->use_decoupled && ld % 256 == 0 && ld >= h->gen6_min_ld && h->num_sms % 4 == 0) {
         if (h->shared_ok < 0) {
           // the partner pairs of generation 6 poll each other: every CTA of the grid has to be resident at once
           cudaLaunchConfig_t cfg = {};

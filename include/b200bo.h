@@ -107,7 +107,8 @@ int b200bo_set_precision(b200bo_handle h, int prec);
 int b200bo_set_keep_R(b200bo_handle h, int keep);
 /* which tensor-core kernel B200BO_PREC_FAST uses: 6 (default) = generation 5 with two CTA pairs sharing one candidate
  * tile: the r chunks are produced once per pair of pairs, the accumulator super-tiles are dealt to the two pairs and the
- * scratch (half the size) stays in L2 (N % 256 == 0, N >= 1024, all CTAs co-resident; else 5); 5 = CTA pairs, every r chunk computed once per tile into a
+ * scratch is half the size (N % 256 == 0, N >= 4096 -- below that the tiles are too short for the hand-over between the
+ * pairs to pay, B200BO_GEN6_MIN_LD -- and all CTAs co-resident; else 5); 5 = CTA pairs, every r chunk computed once per tile into a
  * scratch by producers that run a tile ahead, all A operands by TMA, per-block accumulator drain (N >= 512, else 4);
  * 4 = CTA pairs + replay of r from an L2-resident scratch, first uses written straight into the A ring;
  * 3 = CTA pairs (tcgen05 cta_group::2) sharing the B operands, r recomputed per accumulator super-tile;
@@ -260,6 +261,8 @@ int b200bo_debug_fast_check(b200bo_handle h, int64_t stride, int64_t max_samples
  *   B200BO_FAST_PRODUCTS=1|3     fp16 products per MAC of the first acquisition pass (default 1)
  *   B200BO_REPLAY_MB=n           scratch budget of generation 4 (default 64)
  *   B200BO_CHOL_LOOKAHEAD=0|1|2  Cholesky: single stream | look-ahead, separate kernels | fused panel step where faster
+ *   B200BO_GEN6_MIN_LD=n         smallest padded N for which generation 6 replaces generation 5 (default 4096)
+ *   B200BO_ASSEMBLE_TMA=0|1      kernel-matrix assembly: first version | TMA-staged, specialised per kernel (default 1)
  *   B200BO_CHOL_TC=0|7|8         Cholesky trailing updates on tcgen05 int8 digit planes (= b200bo_set_chol_tc)
  *   B200BO_CHOL_TC_MIN_ROWS=n    smallest trailing matrix that takes the tensor-core update (default 1024)
  *   B200BO_GRAPHS=0|1            CUDA-graph replay of the factorisation stretches for N <= 2048 (default 1)
