@@ -204,6 +204,7 @@ struct b200bo_ctx {
   bool use_shared = false;    // generation 6 applies to this fit (ld % 256 == 0, ld >= 1024, all CTAs co-resident)
   int shared_ok = -1;         // occupancy query of generation 6: -1 not asked yet, 0 no, 1 yes
   DevBuf<uint32_t> share_flags, smid_dbg;
+  int gen6_cooperative = 1;   // B200BO_GEN6_COOPERATIVE=0: plain launch (A/B)
   int gen6_min_ld = 4096;     // smallest padded N generation 6 is used for (B200BO_GEN6_MIN_LD)
   int last_gen = 0;           // generation of the fused kernel the last tensor-core launch used (timings[10])
   cudaStream_t copy_stream = nullptr;
@@ -508,6 +509,7 @@ int b200bo_create(int device, b200bo_handle* out) {
   if (const char* e = getenv("B200BO_CHOL_LOOKAHEAD")) h->lookahead = std::max(0, std::min(2, atoi(e)));
   if (const char* e = getenv("B200BO_GRAPHS")) h->use_graphs = atoi(e) != 0;
   if (const char* e = getenv("B200BO_GEN6_MIN_LD")) h->gen6_min_ld = std::max(1024, atoi(e));
+  if (const char* e = getenv("B200BO_GEN6_COOPERATIVE")) h->gen6_cooperative = atoi(e) != 0;
   if (const char* e = getenv("B200BO_ASSEMBLE_TMA")) h->assemble_tma = atoi(e) != 0;
   if (const char* e = getenv("B200BO_CHOL_TC")) { int v = atoi(e); h->chol_tc = (v == 7 || v == 8) ? v : 0; }
   if (const char* e = getenv("B200BO_CHOL_TC_MIN_ROWS")) h->chol_tc_min_rows = std::max(64, atoi(e));
@@ -1916,7 +1918,16 @@ static int launch_fused(b200bo_handle h, const double* xc_dev, long long m, size
     auto kern = nprod == 1 ? fk6::predict_fused_shared_kernel<C, 1, false> : fk6::predict_fused_shared_kernel<C, 3, false>; \
     if (C == MATERN52 && nprod == 1 && a.trace) kern = fk6::predict_fused_shared_kernel<MATERN52, 1, true>; /* developer timeline */ \
     CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fk6::SMEM6_BYTES));             \
-    kern<<<grid6, fk6::NT6, fk6::SMEM6_BYTES, h->stream>>>(h->replay_maps, a, ra, sa);                              \
+    /* the sides of a group wait for each other: a COOPERATIVE launch, so that the driver refuses a grid it cannot   \
+       make co-resident instead of letting it deadlock into the kernel's timeout traps */                            \
+    cudaLaunchConfig_t cfg6 = {};                                                                                  \
+    cfg6.gridDim = dim3(grid6); cfg6.blockDim = dim3(fk6::NT6); cfg6.dynamicSmemBytes = fk6::SMEM6_BYTES;          \
+    cfg6.stream = h->stream;                                                                                       \
+    cudaLaunchAttribute at6[1];                                                                                    \
+    at6[0].id = cudaLaunchAttributeCooperative;                                                                    \
+    at6[0].val.cooperative = h->gen6_cooperative;                                                                  \
+    cfg6.attrs = at6; cfg6.numAttrs = 1;                                                                           \
+    CU_TRY(cudaLaunchKernelEx(&cfg6, kern, h->replay_maps, a, ra, sa));                                            \
   } while (0)
       switch (h->corr) {
         case RBF: FK6_LAUNCH(RBF); break;
