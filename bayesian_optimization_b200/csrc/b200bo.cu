@@ -204,6 +204,8 @@ struct b200bo_ctx {
   bool use_shared = false;    // generation 6 applies to this fit (ld % 256 == 0, ld >= 1024, all CTAs co-resident)
   int shared_ok = -1;         // occupancy query of generation 6: -1 not asked yet, 0 no, 1 yes
   DevBuf<uint32_t> share_flags, smid_dbg;
+  int fast_max_sms = 1 << 20; // B200BO_FAST_MAX_SMS: cap on the CTAs of the generation-6 grid (developer: scratch size vs SM count)
+  int gen6_db_chunks = 0;     // B200BO_GEN6_DB_CHUNKS: leading chunks of a tile with two scratch slots (generation 6)
   int gen6_cooperative = 1;   // B200BO_GEN6_COOPERATIVE=0: plain launch (A/B)
   int gen6_min_ld = 4096;     // smallest padded N generation 6 is used for (B200BO_GEN6_MIN_LD)
   int last_gen = 0;           // generation of the fused kernel the last tensor-core launch used (timings[10])
@@ -510,6 +512,8 @@ int b200bo_create(int device, b200bo_handle* out) {
   if (const char* e = getenv("B200BO_GRAPHS")) h->use_graphs = atoi(e) != 0;
   if (const char* e = getenv("B200BO_GEN6_MIN_LD")) h->gen6_min_ld = std::max(1024, atoi(e));
   if (const char* e = getenv("B200BO_GEN6_COOPERATIVE")) h->gen6_cooperative = atoi(e) != 0;
+  if (const char* e = getenv("B200BO_GEN6_DB_CHUNKS")) h->gen6_db_chunks = std::max(0, atoi(e));
+  if (const char* e = getenv("B200BO_FAST_MAX_SMS")) h->fast_max_sms = std::max(4, atoi(e));
   if (const char* e = getenv("B200BO_ASSEMBLE_TMA")) h->assemble_tma = atoi(e) != 0;
   if (const char* e = getenv("B200BO_CHOL_TC")) { int v = atoi(e); h->chol_tc = (v == 7 || v == 8) ? v : 0; }
   if (const char* e = getenv("B200BO_CHOL_TC_MIN_ROWS")) h->chol_tc_min_rows = std::max(64, atoi(e));
@@ -1881,7 +1885,8 @@ static int launch_fused(b200bo_handle h, const double* xc_dev, long long m, size
       h->last_gen = 6;
       fk4::ReplayArgs ra;
       ra.scratch = h->r_scratch.p;
-      ra.n_store = h->ld / fk::KC;
+      const int kdb6 = std::max(0, std::min(h->gen6_db_chunks, h->ld / fk::KC)) & ~3;
+      ra.n_store = h->ld / fk::KC + kdb6;   // slots per 128-candidate half (the scratch is sized for generation 5: 2 x nch per pair)
       h->last_n_store = ra.n_store;
       // deal the accumulator super-tiles to the two sides of a group: largest first, to the side that carries less
       const int n_super = (h->ld + fk2::WC - 1) / fk2::WC;
@@ -1895,7 +1900,7 @@ static int launch_fused(b200bo_handle h, const double* xc_dev, long long m, size
       }
       fk6::ShareArgs sa;
       const long long ptiles = (tiles + 1) / 2;
-      const int groups = (int)std::min<long long>(h->num_sms / 4, ptiles);
+      const int groups = (int)std::min<long long>(std::min(h->num_sms, h->fast_max_sms) / 4, ptiles);
       const int grid6 = 4 * groups;
       const size_t nflags = (size_t)groups * 2 * 2 * 3 * 8;
       CU_TRY(h->share_flags.reserve((size_t)(h->num_sms / 4) * 2 * 2 * 3 * 8));
@@ -1908,6 +1913,7 @@ static int launch_fused(b200bo_handle h, const double* xc_dev, long long m, size
       sa.flags = h->share_flags.p;
       sa.side_mask = mask;
       sa.dead_hint = getenv("B200BO_GEN6_DEAD_HINT") ? atoi(getenv("B200BO_GEN6_DEAD_HINT")) : 0;
+      sa.kdb = kdb6;
       sa.smid_out = nullptr;
       if (getenv("B200BO_SMID_DUMP")) {  // developer: where did the CTAs land?
         CU_TRY(h->smid_dbg.reserve(h->num_sms));

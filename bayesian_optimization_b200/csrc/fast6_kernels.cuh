@@ -50,6 +50,8 @@ struct ShareArgs {
   uint32_t* flags;     // (groups, 2 ranks, 2 sides, 3 counters) x 8 words (one 32-byte sector per counter), zeroed per launch
   uint32_t side_mask;  // bit s = side that owns accumulator super-tile s
   int dead_hint;       // 1: the last replay of a chunk is loaded with L2::evict_first (generation 5's habit)
+  int kdb;             // the first kdb chunks of a tile have TWO scratch slots (tile parity): their production for the next
+                       // tile does not wait for this tile's replays (0 = every chunk has one slot)
   uint32_t* smid_out;  // NULL, or (gridDim.x,): the SM every CTA ran on (developer: placement of the partner pairs)
 };
 
@@ -143,7 +145,12 @@ predict_fused_shared_kernel(const __grid_constant__ fk4::ReplayMaps rmaps, const
   const long long n_ptiles = (n_tiles + 1) / 2;  // the group works on tiles 2 pt and 2 pt + 1
   auto LBAR = [&](int i) { return map_to_cta(BAR(i), 0); };
   const int scr_cta = (int)group * 2 + (int)rank;   // the scratch region of this 128-candidate half (shared by both sides)
-  auto scr_row = [&](int kc, int plane) { return ((scr_cta * nch + kc) * PLANES + plane) * BM; };
+  // scratch slot of chunk kc in local tile tl: the first kdb chunks alternate between two slots
+  const int kdb = sh.kdb, nslot = nch + kdb;
+  auto scr_row = [&](int kc, int plane, uint32_t tl) {
+    const int slot = kc < kdb ? 2 * kc + (int)(tl & 1u) : kc + kdb;
+    return ((scr_cta * nslot + slot) * PLANES + plane) * BM;
+  };
   // global counters of the two sides for this half: [0] chunks by producer group 0, [1] by group 1, [2] consumed uses
   uint32_t* const fl_me = sh.flags + (size_t)((scr_cta * 2 + (int)side) * 3) * 8;
   uint32_t* const fl_ot = sh.flags + (size_t)((scr_cta * 2 + (int)(side ^ 1u)) * 3) * 8;
@@ -156,7 +163,7 @@ predict_fused_shared_kernel(const __grid_constant__ fk4::ReplayMaps rmaps, const
     sh.smid_out[blockIdx.x] = smid;
   }
   if (threadIdx.x == 0) {
-    if ((sbase & 1023u) || ra.n_store < nch || nch < 16 || (nch & 3) || me.n == 0 || ot.n == 0) {
+    if ((sbase & 1023u) || ra.n_store < nslot || nch < 16 || (nch & 3) || me.n == 0 || ot.n == 0 || kdb < 0 || kdb > nch) {
       atomicExch(p.err, 97);
       __trap();
     }
@@ -237,7 +244,6 @@ predict_fused_shared_kernel(const __grid_constant__ fk4::ReplayMaps rmaps, const
           const int row_b1 = n0 + (int)rank * (NBA / 2), row_b2 = n0 + NBA + (int)rank * (NBB / 2);
           const uint64_t pol_a = (s == n_super - 1 && sh.dead_hint) ? pol_dead : pol_norm;
           const uint32_t bulk_bytes = a_bytes + (uint32_t)((BA_PLANE + (act_2 ? BB_PLANE : 0)) * PLANES);
-          const int srow0 = scr_row(0, 0), srow_step = PLANES * BM;
           auto bulk = [&](const uint32_t stg, const uint32_t parity, const int kc) {
             const int k0 = kc * KC;
             mbar_wait_fast(BAR(BAR_EMPTY_ST + stg), parity, p.err, 1);
@@ -246,8 +252,9 @@ predict_fused_shared_kernel(const __grid_constant__ fk4::ReplayMaps rmaps, const
             const uint32_t da = sbase + OFF_A + stg * A_STRIDE;
             const uint32_t dst = sbase + OFF_B + stg * B_STRIDE;
             mbar_expect_tx_cluster_p(fb, bulk_bytes, el);
-            tma_load_2d_pair_hint(da, &rmaps.scr, 0, srow0 + kc * srow_step, fb, pol_a, el);
-            if (NPROD == 3) tma_load_2d_pair_hint(da + A_HALF_BYTES, &rmaps.scr, 0, srow0 + kc * srow_step + BM, fb, pol_a, el);
+            const int srow = scr_row(kc, 0, tl);
+            tma_load_2d_pair_hint(da, &rmaps.scr, 0, srow, fb, pol_a, el);
+            if (NPROD == 3) tma_load_2d_pair_hint(da + A_HALF_BYTES, &rmaps.scr, 0, srow + BM, fb, pol_a, el);
             tma_load_2d_pair_hint(dst, &maps.hi128, k0, row_b1, fb, pol_keep, el);
             if (NPROD == 3) tma_load_2d_pair_hint(dst + BOFF_A_LO, &maps.lo128, k0, row_b1, fb, pol_keep, el);
             if (act_2) {
@@ -298,8 +305,8 @@ predict_fused_shared_kernel(const __grid_constant__ fk4::ReplayMaps rmaps, const
             const bool act_1 = !act_01 && k0 < n0 + 256;
             const uint32_t bbytes = (uint32_t)((act_01 ? BA_PLANE : 0) + (act_1 ? BB_PLANE : 0) + (act_2 ? BB_PLANE : 0)) * (uint32_t)PLANES;
             mbar_expect_tx_cluster_p(fb, bbytes + a_bytes, el);
-            tma_load_2d_pair_p(da, &rmaps.scr, 0, scr_row(kc, 0), fb, el);
-            if (NPROD == 3) tma_load_2d_pair_p(da + A_HALF_BYTES, &rmaps.scr, 0, scr_row(kc, 1), fb, el);
+            tma_load_2d_pair_p(da, &rmaps.scr, 0, scr_row(kc, 0, tl), fb, el);
+            if (NPROD == 3) tma_load_2d_pair_p(da + A_HALF_BYTES, &rmaps.scr, 0, scr_row(kc, 1, tl), fb, el);
             if (act_01) {
               tma_load_2d_pair_p(dst, &maps.hi128, k0, row_b1, fb, el);
               if (NPROD == 3) tma_load_2d_pair_p(dst + BOFF_A_LO, &maps.lo128, k0, row_b1, fb, el);
@@ -642,16 +649,18 @@ predict_fused_shared_kernel(const __grid_constant__ fk4::ReplayMaps rmaps, const
         tmem_ld_wait();
         tc_fence_before();
         // the scratch slot of this chunk is free once BOTH sides have retired the previous tile's last replay of it
-        if (elected && tl > 0) {
-          spin_until_ge(cons_cnt, dead_after(me, tl, kc), p.err, 15);
-          spin_until_ge(mir + 8u, dead_after(ot, tl, kc), p.err, 17);
+        // (a double-buffered chunk reuses the slot of tile tl - 2)
+        const uint32_t tw = kc < kdb ? tl - 1u : tl;
+        if (elected && tl > (kc < kdb ? 1u : 0u)) {
+          spin_until_ge(cons_cnt, dead_after(me, tw, kc), p.err, 15);
+          spin_until_ge(mir + 8u, dead_after(ot, tw, kc), p.err, 17);
         }
         if (grp == 0) asm volatile("bar.sync 1, %0;" ::"n"(32 * NPW / 2) : "memory");
         else asm volatile("bar.sync 2, %0;" ::"n"(32 * NPW / 2) : "memory");
         if (elected) mbar_arrive_leader(BAR(BAR_EMPTY_G + grp), leader);
         if (tr) p.trace[j * 8 + 5] = clock64();
-        uint8_t* g_hi = scr + ((size_t)scr_row(kc, 0) + (size_t)m) * 128;
-        uint8_t* g_lo = scr + ((size_t)scr_row(kc, PLANES - 1) + (size_t)m) * 128;
+        uint8_t* g_hi = scr + ((size_t)scr_row(kc, 0, tl) + (size_t)m) * 128;
+        uint8_t* g_lo = scr + ((size_t)scr_row(kc, PLANES - 1, tl) + (size_t)m) * 128;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int col0 = 32 * ch + 16 * h;
