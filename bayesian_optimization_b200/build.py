@@ -40,6 +40,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     srcs = sources()
     if force or not _newer(LIB, srcs):
         dev = ["-DB200BO_DEV_KERNELS"] if os.environ.get("B200BO_DEV_KERNELS") == "1" else []  # + the superseded generations 2, 3
+        dev += ["-D" + d for d in os.environ.get("B200BO_EXTRA_DEFINES", "").split() if d]             # A/B builds
         cmd = [nvcc, *NVCC_FLAGS, *dev, "-o", LIB, os.path.join(CSRC, "b200bo.cu")]
         r = subprocess.run(cmd, capture_output=True, text=True)
         log = r.stdout + r.stderr
