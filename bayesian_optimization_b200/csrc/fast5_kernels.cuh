@@ -135,6 +135,23 @@ __device__ __forceinline__ void mbar_wait_fast(uint32_t bar, uint32_t parity, in
   if (!mbar_try_wait(bar, parity)) mbar_wait(bar, parity, err, code);
 }
 
+// corr_from_acc (fast2_kernels.cuh) on two values: the polynomial part in packed fp32, the MUFU calls per value
+template <int CORR>
+__device__ __forceinline__ float2 corr2_from_acc(float2 acc) {
+  const float2 c14 = make_float2((float)A_SCALE_LOG2, (float)A_SCALE_LOG2);
+  if (CORR == RBF) {
+    const float2 a = __ffma2_rn(acc, make_float2(-1.f, -1.f), c14);
+    return make_float2(ex2_approx(a.x), ex2_approx(a.y));
+  }
+  const float2 t = make_float2(sqrt_approx(acc.x), sqrt_approx(acc.y));
+  const float2 a = __ffma2_rn(t, make_float2(-1.4426950408889634f, -1.4426950408889634f), c14);
+  const float2 e = make_float2(ex2_approx(a.x), ex2_approx(a.y));
+  if (CORR == MATERN12) return e;
+  if (CORR == MATERN32) return __ffma2_rn(t, e, e);
+  const float2 q = __ffma2_rn(acc, make_float2(1.0f / 3.0f, 1.0f / 3.0f), __fadd2_rn(make_float2(1.f, 1.f), t));
+  return __fmul2_rn(q, e);  // MATERN52
+}
+
 template <int CORR, int NPROD, bool TRACE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT2, 1)
 predict_fused_decoupled_kernel(const __grid_constant__ fk4::ReplayMaps rmaps, const Fused2Args p, const fk4::ReplayArgs ra) {
@@ -564,7 +581,7 @@ predict_fused_decoupled_kernel(const __grid_constant__ fk4::ReplayMaps rmaps, co
         mbar_wait(BAR(BAR_FULL_G + grp), (j / 2) & 1, p.err, 10);
         tc_fence_after();
         if (tr) p.trace[j * 8 + 4] = clock64();
-        float ysum = 0.f, fsum = 0.f;
+        float2 ys2 = make_float2(0.f, 0.f), fs2 = make_float2(0.f, 0.f);
         // read the whole Gram row segment first and hand the TMEM block back: the Gram MMA of chunk j + 2 then
         // runs while this group is still computing
         uint32_t gr0[16], gr1[16];
@@ -588,18 +605,25 @@ predict_fused_decoupled_kernel(const __grid_constant__ fk4::ReplayMaps rmaps, co
           float bj[16];
 #pragma unroll
           for (int i = 0; i < 16; i += 4) *(float4*)&bj[i] = *(const float4*)(aux + i);
+          // two values per instruction (FFMA2 / FADD2 / FMUL2), as in generation 6
           float kv[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float acc = fmaxf(fmaf(CG, __uint_as_float(gr[i]), am + bj[i]), 0.f);
-            kv[i] = corr_from_acc<CORR>(acc);
+          for (int i = 0; i < 16; i += 2) {
+            const float2 g2 = make_float2(__uint_as_float(gr[i]), __uint_as_float(gr[i + 1]));
+            float2 a2 = __ffma2_rn(make_float2(CG, CG), g2, __fadd2_rn(make_float2(am, am), make_float2(bj[i], bj[i + 1])));
+            a2.x = fmaxf(a2.x, 0.f);
+            a2.y = fmaxf(a2.y, 0.f);
+            const float2 k2 = corr2_from_acc<CORR>(a2);
+            kv[i] = k2.x;
+            kv[i + 1] = k2.y;
           }
 #pragma unroll
           for (int i = 0; i < 16; i += 4) {
             const float4 gj = *(const float4*)(aux + KC + i);
             const float4 fj = *(const float4*)(aux + 2 * KC + i);
-            ysum = fmaf(kv[i], gj.x, fmaf(kv[i + 1], gj.y, fmaf(kv[i + 2], gj.z, fmaf(kv[i + 3], gj.w, ysum))));
-            fsum = fmaf(kv[i], fj.x, fmaf(kv[i + 1], fj.y, fmaf(kv[i + 2], fj.z, fmaf(kv[i + 3], fj.w, fsum))));
+            const float2 ka = make_float2(kv[i], kv[i + 1]), kb = make_float2(kv[i + 2], kv[i + 3]);
+            ys2 = __ffma2_rn(ka, make_float2(gj.x, gj.y), __ffma2_rn(kb, make_float2(gj.z, gj.w), ys2));
+            fs2 = __ffma2_rn(ka, make_float2(fj.x, fj.y), __ffma2_rn(kb, make_float2(fj.z, fj.w), fs2));
           }
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
@@ -620,8 +644,8 @@ predict_fused_decoupled_kernel(const __grid_constant__ fk4::ReplayMaps rmaps, co
             if (NPROD == 3) *(uint4*)(g_lo + goff) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           }
         }
-        ysum_d += (double)ysum;
-        fsum_d += (double)fsum;
+        ysum_d += (double)(ys2.x + ys2.y);
+        fsum_d += (double)(fs2.x + fs2.y);
         asm volatile("fence.proxy.async.global;" ::: "memory");  // scratch stores -> visible to the TMA loads
         if (tr) p.trace[j * 8 + 6] = clock64();
         if (grp == 0) asm volatile("bar.sync 1, %0;" ::"n"(32 * NPW / 2) : "memory");

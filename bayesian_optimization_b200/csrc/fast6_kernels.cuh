@@ -85,23 +85,6 @@ __device__ __forceinline__ void spin_until_ge_gpu(const uint32_t* p, uint32_t ne
   }
 }
 
-// corr_from_acc (fast2_kernels.cuh) on two values: the polynomial part in packed fp32, the MUFU calls per value
-template <int CORR>
-__device__ __forceinline__ float2 corr2_from_acc(float2 acc) {
-  const float2 c14 = make_float2((float)A_SCALE_LOG2, (float)A_SCALE_LOG2);
-  if (CORR == RBF) {
-    const float2 a = __ffma2_rn(acc, make_float2(-1.f, -1.f), c14);
-    return make_float2(ex2_approx(a.x), ex2_approx(a.y));
-  }
-  const float2 t = make_float2(sqrt_approx(acc.x), sqrt_approx(acc.y));
-  const float2 a = __ffma2_rn(t, make_float2(-1.4426950408889634f, -1.4426950408889634f), c14);
-  const float2 e = make_float2(ex2_approx(a.x), ex2_approx(a.y));
-  if (CORR == MATERN12) return e;
-  if (CORR == MATERN32) return __ffma2_rn(t, e, e);
-  const float2 q = __ffma2_rn(acc, make_float2(1.0f / 3.0f, 1.0f / 3.0f), __fadd2_rn(make_float2(1.f, 1.f), t));
-  return __fmul2_rn(q, e);  // MATERN52
-}
-
 // what one side does per tile: its super-tiles (bits of `mine`), chunk uses per tile, uses of its last super-tile
 struct SidePlan {
   uint32_t mine;  // bit s set = super-tile s is this side's
