@@ -204,6 +204,7 @@ struct b200bo_ctx {
   bool use_shared = false;    // generation 6 applies to this fit (ld % 256 == 0, ld >= 1024, all CTAs co-resident)
   int shared_ok = -1;         // occupancy query of generation 6: -1 not asked yet, 0 no, 1 yes
   DevBuf<uint32_t> share_flags, smid_dbg;
+  int rescore_max = 2048;     // B200BO_RESCORE_MAX: a one-product band up to max(this, M / 50) candidates is re-scored directly
   int fast_max_sms = 1 << 20; // B200BO_FAST_MAX_SMS: cap on the CTAs of the generation-6 grid (developer: scratch size vs SM count)
   int gen6_db_chunks = 0;     // B200BO_GEN6_DB_CHUNKS: leading chunks of a tile with two scratch slots (generation 6)
   int gen6_cooperative = 1;   // B200BO_GEN6_COOPERATIVE=0: plain launch (A/B)
@@ -514,6 +515,7 @@ int b200bo_create(int device, b200bo_handle* out) {
   if (const char* e = getenv("B200BO_GEN6_COOPERATIVE")) h->gen6_cooperative = atoi(e) != 0;
   if (const char* e = getenv("B200BO_GEN6_DB_CHUNKS")) h->gen6_db_chunks = std::max(0, atoi(e));
   if (const char* e = getenv("B200BO_FAST_MAX_SMS")) h->fast_max_sms = std::max(4, atoi(e));
+  if (const char* e = getenv("B200BO_RESCORE_MAX")) h->rescore_max = std::max(1, atoi(e));
   if (const char* e = getenv("B200BO_ASSEMBLE_TMA")) h->assemble_tma = atoi(e) != 0;
   if (const char* e = getenv("B200BO_CHOL_TC")) { int v = atoi(e); h->chol_tc = (v == 7 || v == 8) ? v : 0; }
   if (const char* e = getenv("B200BO_CHOL_TC_MIN_ROWS")) h->chol_tc_min_rows = std::max(64, atoi(e));
@@ -2055,8 +2057,13 @@ static int check_fast_err(b200bo_handle h) {
   return 0;
 }
 
-static const int FAST_CHUNK_TILES = 8;        // candidate tiles per SM per fused launch when streaming from the host
-static const int RESCORE_DIRECT_MAX = 2048;   // widest one-product band that goes straight to the fp64 re-score
+static const int FAST_CHUNK_TILES = 8;        // candidate tiles per SM per fused launch when streaming from the host (at N = 4096)
+// launches are sized in time, not tiles: (4096 / ld)^2 more tiles per launch below N = 4096
+static inline int64_t chunk_scale(int ld) {
+  if (ld >= 4096) return 1;
+  const int64_t r = (4096 + ld - 1) / ld;
+  return r * r;
+}
 static const int LIST0_CAP = 1 << 16;         // scan survivors (~ subsample stride x q when the criterion is not flat)
 static const int THR_STRIDE = 32;
 static const double MODEL_LAMBDA = 8.0;       // the a-priori half-widths sit MODEL_LAMBDA modelled standard deviations out
@@ -2137,7 +2144,9 @@ static int fast_pass(b200bo_handle h, const double* Xc, int64_t M, bool dev, int
   *launches = 0;
   if (dev) {
     *xdev = Xc;
-    const int64_t chunk = h->dev_chunk_tiles > 0 ? (int64_t)h->num_sms * fk::BM * h->dev_chunk_tiles : M;
+    // tiles per SM and launch: the knob is quoted at N = 4096 (8 tiles ~ 2.2 ms per launch) and scaled so that a launch
+    // stays that long at smaller N -- a fixed 8 tiles cost C2 (N = 1024) a factor two in seven 0.5 ms launches
+    const int64_t chunk = h->dev_chunk_tiles > 0 ? (int64_t)h->num_sms * fk::BM * h->dev_chunk_tiles * chunk_scale(h->ld) : M;
     for (int64_t a = 0; a < M; a += chunk) {
       if ((rc = launch_fused(h, Xc + (size_t)a * D, std::min<int64_t>(chunk, M - a), (size_t)a, nprod))) return rc;
       ++*launches;
@@ -2146,7 +2155,7 @@ static int fast_pass(b200bo_handle h, const double* Xc, int64_t M, bool dev, int
   }
   CU_TRY(h->Xall.reserve((size_t)M * D));
   *xdev = h->Xall.p;
-  const int64_t FMc = (int64_t)h->num_sms * fk::BM * FAST_CHUNK_TILES;
+  const int64_t FMc = (int64_t)h->num_sms * fk::BM * FAST_CHUNK_TILES * chunk_scale(h->ld);
   // the buffer may still be read by earlier work of the compute stream
   CU_TRY(cudaEventRecord(h->ev_used[0], st));
   CU_TRY(cudaStreamWaitEvent(h->copy_stream, h->ev_used[0], 0));
@@ -2265,10 +2274,14 @@ static int run_candidates_fast(b200bo_handle h, const double* Xc, int64_t M, int
   const int nslices = ld / bd::KSS_COLS + (ld % bd::KSS_COLS ? 1 : 0);
   const int rd_blocks = ld / bd::RD_WARPS, rd_grid = std::min(rd_blocks, h->num_sms * 2);
   CU_TRY(h->thr_key.reserve(2 * (size_t)q));
-  CU_TRY(h->band_list0.reserve(LIST0_CAP));
-  CU_TRY(h->band_list.reserve(LIST0_CAP));
+  // capacity of the scan's survivor list: the 1/32-subsample threshold lets through ~ stride x q candidates when the
+  // criterion is peaked, but several per cent of M when it is not (C2, EI: 78 672 of 1e6, of which 244 form the band);
+  // 2^18 entries where q is small (the exact-bound table is cap x q doubles), 2^16 at q = 32
+  const int cap0 = (int)std::max<long long>(LIST0_CAP, std::min<long long>(1 << 18, (1LL << 21) / std::max(q, 1)));
+  CU_TRY(h->band_list0.reserve(cap0));
+  CU_TRY(h->band_list.reserve(cap0));
   CU_TRY(h->band_count.reserve(2));
-  CU_TRY(h->band_hiB.reserve((size_t)LIST0_CAP * q));
+  CU_TRY(h->band_hiB.reserve((size_t)cap0 * q));
   CU_TRY(h->Xband.reserve((size_t)Mc * D));
   CU_TRY(h->bd_kst.reserve((size_t)BD * ld));
   CU_TRY(h->bd_ypart.reserve((size_t)nslices * BD));
@@ -2308,12 +2321,12 @@ static int run_candidates_fast(b200bo_handle h, const double* Xc, int64_t M, int
     fk::band_thr0_kernel<<<(int)std::min<long long>(h->num_sms * 4, (ns + 255) / 256), 256, 0, st>>>(b, THR_STRIDE, h->thr_key.p);
     CU_TRY(cudaGetLastError());
     fk::band_scan_kernel<<<(int)std::min<long long>(h->num_sms * 8, (M + 255) / 256), 256, 0, st>>>(
-        b, h->thr_key.p, h->band_list0.p, LIST0_CAP, h->band_count.p);
+        b, h->thr_key.p, h->band_list0.p, cap0, h->band_count.p);
     CU_TRY(cudaGetLastError());
-    fk::band_refine_kernel<<<h->num_sms, 256, 0, st>>>(b, h->band_list0.p, h->band_count.p, LIST0_CAP, h->band_hiB.p,
+    fk::band_refine_kernel<<<h->num_sms, 256, 0, st>>>(b, h->band_list0.p, h->band_count.p, cap0, h->band_hiB.p,
                                                        h->thr_key.p + q);
     CU_TRY(cudaGetLastError());
-    fk::band_filter_kernel<<<h->num_sms, 256, 0, st>>>(h->band_list0.p, h->band_count.p, LIST0_CAP, h->band_hiB.p,
+    fk::band_filter_kernel<<<h->num_sms, 256, 0, st>>>(h->band_list0.p, h->band_count.p, cap0, h->band_hiB.p,
                                                        h->thr_key.p + q, q, h->band_list.p, h->band_count.p + 1);
     CU_TRY(cudaGetLastError());
     // exact float64 re-score of up to BAND_DEV_MAX band members, sizes read on the device
@@ -2361,13 +2374,19 @@ static int run_candidates_fast(b200bo_handle h, const double* Xc, int64_t M, int
     if (pin_ctl->fused_err)
       return set_err(B200BO_E_CUDA, "tensor-core pipeline wait timed out (code " + std::to_string(pin_ctl->fused_err) + ")");
     const int count0 = pin_ctl->count0, count = pin_ctl->count;
-    if (nprod == 1 && (count0 > LIST0_CAP || count > RESCORE_DIRECT_MAX || passes > 2)) {
+    // Escalate from one product to three only where that is the cheaper way to a narrow band: re-scoring `count`
+    // candidates in float64 costs ~count x N^2 flops on the fp64 pipe (~20 TFLOP/s), the two extra products ~2 M N^2 on
+    // the tensor pipe (~1000 TFLOP/s) -- break-even at count ~ M / 25.  (A fixed 2048 sent C2, whose a-priori half-widths
+    // admit a few thousand of its 1e6 candidates, to the three-product pass: 3.4 ms per step instead of 1.5.)
+    const long long rescore_max = std::max<long long>(h->rescore_max, M / 50);
+    if (getenv("B200BO_BAND_DEBUG")) fprintf(stderr, "band: nprod %d pass %d count0 %d count %d (direct up to %lld)\n", nprod, passes, count0, count, rescore_max);
+    if (nprod == 1 && (count0 > cap0 || count > rescore_max || passes > 2)) {
       // the one-product pass cannot separate the top of this criterion: three products for the rest of this fit
       h->escalate = true;
       return run_candidates_fast(h, Xc, M, loc, eval_mse, yhat_out, mse_out, acq_id, minimize, plugin, params, q,
                                  best_val, best_idx, fell_back);
     }
-    if (count0 > LIST0_CAP || passes > 4) {  // degenerate (flat criterion) or unstable error estimate
+    if (count0 > cap0 || passes > 4) {  // degenerate (flat criterion) or unstable error estimate
       *fell_back = true;
       return 0;
     }
