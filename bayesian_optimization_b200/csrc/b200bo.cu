@@ -1916,6 +1916,7 @@ static int launch_fused(b200bo_handle h, const double* xc_dev, long long m, size
       sa.side_mask = mask;
       sa.dead_hint = getenv("B200BO_GEN6_DEAD_HINT") ? atoi(getenv("B200BO_GEN6_DEAD_HINT")) : 0;
       sa.kdb = kdb6;
+      sa.trace_cta = getenv("B200BO_TRACE_CTA") ? atoi(getenv("B200BO_TRACE_CTA")) : 0;
       sa.smid_out = nullptr;
       if (getenv("B200BO_SMID_DUMP")) {  // developer: where did the CTAs land?
         CU_TRY(h->smid_dbg.reserve(h->num_sms));

@@ -50,6 +50,7 @@ struct ShareArgs {
   uint32_t* flags;     // (groups, 2 ranks, 2 sides, 3 counters) x 8 words (one 32-byte sector per counter), zeroed per launch
   uint32_t side_mask;  // bit s = side that owns accumulator super-tile s
   int dead_hint;       // 1: the last replay of a chunk is loaded with L2::evict_first (generation 5's habit)
+  int trace_cta;       // developer timeline: which CTA writes it (0 = side 0 of group 0, 2 = side 1)
   int kdb;             // the first kdb chunks of a tile have TWO scratch slots (tile parity): their production for the next
                        // tile does not wait for this tile's replays (0 = every chunk has one slot)
   uint32_t* smid_out;  // NULL, or (gridDim.x,): the SM every CTA ran on (developer: placement of the partner pairs)
@@ -426,7 +427,7 @@ predict_fused_shared_kernel(const __grid_constant__ fk4::ReplayMaps rmaps, const
             const int k0 = ci < n_bulk ? 0 : ci * KC;     // any chunk under the diagonal blocks behaves like k0 = 0
             const bool first = ci == 0;
             const uint32_t nst = (st + 1) & (ST - 1), nph = ph ^ (nst == 0 ? 1u : 0u);
-            const bool tr = TRACE && p.trace && blockIdx.x == 0 && ic < (uint32_t)TRACE5_CHUNKS && lane == 0;
+            const bool tr = TRACE && p.trace && (int)blockIdx.x == sh.trace_cta && ic < (uint32_t)TRACE5_CHUNKS && lane == 0;
             if (tr) p.trace[ic * 8 + 0] = clock64();
             const uint64_t da_hi = da0 + A_STEP * st, da_lo = da_hi + (A_HALF_BYTES >> 4);
             const uint64_t db_hi = db0 + B_STEP * st, db_lo = db_hi + (BOFF_A_LO >> 4);
@@ -476,7 +477,7 @@ predict_fused_shared_kernel(const __grid_constant__ fk4::ReplayMaps rmaps, const
           };
           // ---- one replayed chunk under the diagonal blocks; stage `stg` (compile-time in the unrolled loop below)
           auto bulk = [&](const uint32_t stg, const uint32_t wait_parity) {
-            const bool tr = TRACE && p.trace && blockIdx.x == 0 && ic < (uint32_t)TRACE5_CHUNKS && lane == 0;
+            const bool tr = TRACE && p.trace && (int)blockIdx.x == sh.trace_cta && ic < (uint32_t)TRACE5_CHUNKS && lane == 0;
             if (tr) p.trace[ic * 8 + 0] = clock64();
             const uint64_t da_hi = da0 + A_STEP * stg, da_lo = da_hi + (A_HALF_BYTES >> 4);
             const uint64_t db_hi = db0 + B_STEP * stg, db_lo = db_hi + (BOFF_A_LO >> 4);
@@ -636,7 +637,7 @@ predict_fused_shared_kernel(const __grid_constant__ fk4::ReplayMaps rmaps, const
         if ((lc & 1) != grp) continue;  // the other group's chunk (nmy is even: chunk parity = j parity)
         const int kc = my_chunk(lc);
         const uint32_t ax = j % AUX_STAGES;
-        const bool tr = TRACE && p.trace && blockIdx.x == 0 && j < (uint32_t)TRACE5_CHUNKS && pw == 0 && lane == 0;
+        const bool tr = TRACE && p.trace && (int)blockIdx.x == sh.trace_cta && j < (uint32_t)TRACE5_CHUNKS && pw == 0 && lane == 0;
         if (tr) p.trace[j * 8 + 3] = clock64();
         mbar_wait(BAR(BAR_FULL_AUX + ax), (j / AUX_STAGES) & 1, p.err, 11);
         mbar_wait(BAR(BAR_FULL_G + grp), (j / 2) & 1, p.err, 10);
